@@ -1,0 +1,215 @@
+/*
+ * evgsim.h — C ABI of libevgsim: the batched, GPU-resident Everglades turn step.
+ *
+ * This is the drop-in boundary for ONE path of jlehett/everglades-ai-wargame:
+ *     EvergladesEnv.reset / EvergladesEnv.step
+ *         gym-everglades/gym_everglades/envs/everglades_env.py:32-116   ("env.py")
+ *     -> EvergladesGame.game_init / game_turn / board_state / player_state
+ *         everglades-server/everglades_server/server.py:133-501          ("server.py")
+ * for N matches in lockstep.  The reference has no FFI (it is pure Python); the binding a
+ * maintainer would add is a ctypes stub — see INTEGRATION.md.
+ *
+ * Rules of the boundary
+ *   - plain C types only; no torch / CUDA runtime types in any signature (`stream` is a
+ *     cudaStream_t passed as void*, 0 = the legacy default stream);
+ *   - the library NEVER allocates device memory: the caller asks evg_layout() for sizes,
+ *     allocates (torch.empty / cudaMalloc) and binds raw device pointers with evg_bind();
+ *   - every call is asynchronous on `stream`; nothing synchronises unless stated;
+ *   - every entry point returns 0 on success or a negative EVG_E_* code; evg_last_error()
+ *     returns a thread-local human-readable message for the last failure.
+ *   - there is NO CPU fallback: without a CUDA device evg_create() fails with EVG_E_CUDA.
+ */
+#ifndef EVGSIM_H
+#define EVGSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVG_ABI_VERSION 1
+
+/* compile-time maxima of the state layout */
+#define EVG_MAX_NODES 32       /* node IDs are 1..n_nodes (DemoMap: 11) */
+#define EVG_MAX_UNIT_TYPES 8   /* UnitDefinitions.json entries (reference: 3) */
+#define EVG_NUM_GROUPS 12      /* groups per player, env.py:19 */
+#define EVG_MAX_GROUP_UNITS 16 /* unit slots per group (reference loadout: 8, last group 12) */
+#define EVG_MAX_ACTIONS 7      /* rows of an action array that count, server.py:227 */
+#define EVG_NUM_PLAYERS 2
+
+/* error codes */
+#define EVG_OK 0
+#define EVG_E_ARG -1    /* null pointer / out-of-range argument */
+#define EVG_E_CONFIG -2 /* EvgConfig fails validation (see evg_last_error) */
+#define EVG_E_CUDA -3   /* CUDA runtime error (no device, launch failure, ...) */
+#define EVG_E_STATE -4  /* call sequence error, e.g. step before bind */
+
+/* game status, server.py:284-289 */
+#define EVG_STATUS_IN_PROGRESS 0
+#define EVG_STATUS_TIME_EXPIRED 1
+#define EVG_STATUS_BASE_CAPTURE 2
+#define EVG_STATUS_ANNIHILATION 3
+
+/* what evg_step does with a match whose status != 0 */
+#define EVG_AUTORESET_OFF 0       /* keep stepping it, like the reference server does */
+#define EVG_AUTORESET_TERMINAL 1  /* reset in place; obs of that step = terminal obs (reference-identical) */
+#define EVG_AUTORESET_NEXT 2      /* reset in place; obs of that step = first obs of the new match */
+
+/*
+ * Static game description: DemoMap.json + UnitDefinitions.json + GameSetup.json semantics
+ * (server.py:40-131 board_init/unitTypes_init; env.py:15-22,145-156 constants and loadout).
+ * All per-node arrays are indexed by node ID (entry 0 unused).
+ */
+typedef struct EvgConfig {
+    int32_t abi_version; /* = EVG_ABI_VERSION */
+    int32_t n_nodes;
+    int32_t n_unit_types;
+    int32_t turn_limit;    /* GameSetup.json TurnLimit; hard-coded 150 at server.py:321 */
+    int32_t capture_bonus; /* GameSetup.json CaptureBonus; hard-coded 1000 at server.py:304 */
+    int32_t max_score;     /* reward normaliser MAX_SCORE = 3700, env.py:11 */
+    int32_t auto_reset;    /* EVG_AUTORESET_* */
+    int32_t reserved0;
+
+    int32_t node_control_points[EVG_MAX_NODES + 1]; /* "ControlPoints" */
+    double node_defense[EVG_MAX_NODES + 1];         /* "StructureDefense" */
+    int8_t node_team_start[EVG_MAX_NODES + 1];      /* "TeamStart": -1, 0 or 1 */
+    uint8_t node_has_defense[EVG_MAX_NODES + 1];    /* 'DEFENSE' in Resource: obs flag, server.py:442 */
+    uint8_t node_has_observe[EVG_MAX_NODES + 1];    /* 'OBSERVE' in Resource: obs flag, server.py:443 */
+    uint8_t node_has_defend[EVG_MAX_NODES + 1];     /* 'DEFEND' in Resource: combat bonus, server.py:595
+                                                       (never true on DemoMap, whose maps say "DEFENSE") */
+    /* edge_distance[a][b] = "Distance" of the FIRST connection of node a whose ConnectedID is b
+       (server.py:246-250), 0 = not connected */
+    uint8_t edge_distance[EVG_MAX_NODES + 1][EVG_MAX_NODES + 1];
+    /* player 1's view of node ids (server.py:89); must be an involution with map[0] = 0 */
+    uint8_t p1_node_map[EVG_MAX_NODES + 1];
+
+    double unit_armor[EVG_MAX_UNIT_TYPES];    /* "Health" — used as armour, server.py:592 */
+    int32_t unit_damage[EVG_MAX_UNIT_TYPES];  /* "Damage" */
+    int32_t unit_speed[EVG_MAX_UNIT_TYPES];   /* "Speed" */
+    int32_t unit_control[EVG_MAX_UNIT_TYPES]; /* "Control" */
+    int32_t unit_cost[EVG_MAX_UNIT_TYPES];    /* "Cost" */
+
+    /* loadout, env.py:145-156: type id = index in UnitDefinitions.json (server.py:128-129) */
+    uint8_t group_type[EVG_NUM_PLAYERS][EVG_NUM_GROUPS];
+    uint8_t group_size[EVG_NUM_PLAYERS][EVG_NUM_GROUPS]; /* 1..EVG_MAX_GROUP_UNITS */
+} EvgConfig;
+
+/* One group, as the reference keeps it (definitions.py:35-47 EvgGroup + :58-64 EvgUnit). */
+typedef struct EvgGroupState {
+    int16_t location;           /* node ID */
+    int16_t travel_destination; /* node ID or -1 */
+    int16_t distance_remaining;
+    uint8_t ready;
+    uint8_t moving;
+    uint8_t destroyed;
+    uint8_t count;       /* alive units */
+    int32_t arrival;     /* list-order stamp: groups of one player at one node are listed by
+                            ascending arrival (node.groups[pid], server.py:198,690-691);
+                            canonical value: gid at reset, turn*16+gid on arrival */
+    int32_t avg_health;  /* int(sum(health)/alive) as player_state reports it (server.py:491) */
+} EvgGroupState;
+
+/* One match, array-of-structs view used by evg_export_state / evg_import_state (parity tests,
+ * checkpointing).  The resident device layout is different (see evg_layout). */
+typedef struct EvgEnvState {
+    int32_t turn;    /* current_turn, server.py:140,214 */
+    int32_t episode; /* how many matches this slot has finished or been reset out of; keys the tape
+                        so that successive matches of one slot differ (0 after evg_reset(NULL)) */
+    int16_t control_state[EVG_MAX_NODES + 1]; /* node.controlState, definitions.py:17 */
+    int8_t controlled_by[EVG_MAX_NODES + 1];  /* node.controlledBy, definitions.py:16 */
+    int8_t pad1[5];
+    EvgGroupState groups[EVG_NUM_PLAYERS][EVG_NUM_GROUPS];
+    double health[EVG_NUM_PLAYERS][EVG_NUM_GROUPS][EVG_MAX_GROUP_UNITS]; /* unitHealth, definitions.py:62 */
+} EvgEnvState;
+
+/* Sizes of the device arrays the caller must allocate and bind (bytes, for n_envs matches). */
+typedef struct EvgLayout {
+    int64_t n_envs;
+    int32_t obs_len;       /* per player: 1 + 4*n_nodes + 5*12 (105 on DemoMap), env.py:165-167 */
+    int32_t record_bytes;  /* per match: packed group/node/turn record */
+    int32_t health_slots;  /* per match: fp64 unit-health slots (both players, padded) */
+    int32_t action_bytes;  /* per match: 2*7*2 int8 */
+    int64_t records_bytes; /* = n_envs * record_bytes           (bind slot EVG_BIND_RECORDS) */
+    int64_t health_bytes;  /* = n_envs * health_slots * 8       (bind slot EVG_BIND_HEALTH)  */
+    int64_t stats_bytes;   /* episode statistics accumulators   (bind slot EVG_BIND_STATS)   */
+} EvgLayout;
+
+#define EVG_BIND_RECORDS 0
+#define EVG_BIND_HEALTH 1
+#define EVG_BIND_STATS 2
+#define EVG_BIND_COUNT 3
+
+/* Episode statistics accumulated on the device by evg_step (matches that ended). */
+typedef struct EvgEpisodeStats {
+    int64_t episodes;
+    int64_t wins[2]; /* by final score, the test callers use (evaluate.py:155-160) */
+    int64_t ties;
+    int64_t total_turns;     /* sum of episode lengths */
+    int64_t total_score[2];  /* sum of final scores */
+    int64_t status_count[4]; /* histogram of EVG_STATUS_* at episode end */
+    int64_t env_turns;       /* all match-turns stepped since creation / last clear */
+} EvgEpisodeStats;
+
+typedef struct EvgSim EvgSim; /* opaque */
+
+/* Fill `cfg` with the reference's DemoMap.json / UnitDefinitions.json / GameSetup.json values
+ * and the env.py:145-156 loadout (useful when no JSON parser is at hand). */
+int evg_default_config(EvgConfig* cfg);
+
+/* Validate `cfg` and create a simulator for `n_envs` matches on CUDA device `device`.
+ * Match i has global id env_id_offset + i; the combat tape is keyed on (seed, global id,
+ * turn, node, side, group, unit) so trajectories do not depend on how matches are sharded.
+ * Replaces: EvergladesEnv.__init__ (env.py:15-30) + EvergladesGame.__init__ (server.py:14-38). */
+int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_id_offset, int device,
+               EvgSim** out);
+int evg_destroy(EvgSim* sim);
+
+int evg_layout(const EvgSim* sim, EvgLayout* out);
+/* Bind caller-owned device arrays (index = EVG_BIND_*). Must precede reset/step. */
+int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs);
+
+/* Put matches into the post-game_init state (server.py:133-209, env.py:75-116) and write their
+ * observations.  d_mask: n_envs bytes, non-zero = reset this match; NULL = all.
+ * d_obs: float32 [n_envs][2][obs_len] or NULL.  Also zeroes the statistics when d_mask is NULL. */
+int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
+
+/* One game turn for every match (env.py:32-73 step -> server.py:211-279 game_turn, 281-348
+ * game_end, 382-501 observations).
+ *   d_actions: int8 [n_envs][2][7][2] = (group id, node id in the acting player's numbering);
+ *              rows with group/node out of range are ignored (the reference raises IndexError).
+ *   d_obs:     float32 [n_envs][2][obs_len]   (reference: float64 arrays of integers)
+ *   d_reward:  float32 [n_envs][2]            (env.py:37-60)
+ *   d_done:    uint8   [n_envs]               (status != 0)
+ *   d_status / d_scores: optional (may be NULL): uint8 [n_envs], int32 [n_envs][2]. */
+int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done,
+             uint8_t* d_status, int32_t* d_scores, void* stream);
+
+/* Same turn through HOST buffers: H2D of the actions, the step, D2H of obs/reward/done, all
+ * queued on `stream` (pinned host memory makes them truly asynchronous).  The device staging
+ * arrays are the caller's (same shapes as evg_step). */
+int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done,
+                  int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, void* stream);
+
+/* Array-of-structs snapshot <-> resident layout, matches [first, first+count).  d_states is a
+ * DEVICE array of EvgEnvState (the caller copies it to/from the host). */
+int evg_export_state(EvgSim* sim, int64_t first, int64_t count, EvgEnvState* d_states, void* stream);
+int evg_import_state(EvgSim* sim, int64_t first, int64_t count, const EvgEnvState* d_states, void* stream);
+
+/* Copy the statistics accumulators to the host (synchronises `stream`). */
+int evg_episode_stats(EvgSim* sim, EvgEpisodeStats* host_out, void* stream);
+
+/* On-device scripted opponents (agents/State_Machine, Python files), writing int8 [n_envs][2][7][2]
+ * action rows for `player` (0, 1, or -1 = both).  See DESIGN.md §7 for their tape. */
+int evg_agent_random(EvgSim* sim, int8_t* d_actions, int32_t player, void* stream);
+
+/* Number of kernels this library has launched since creation (bench.py's gpu_launches). */
+int64_t evg_launch_count(const EvgSim* sim);
+
+const char* evg_last_error(void);
+int evg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVGSIM_H */

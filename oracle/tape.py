@@ -1,0 +1,57 @@
+"""Random tape shared by the oracle, the reference harness and the CUDA path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md): nothing under
+``everglades-ai-wargame_b200/`` may import this module.
+
+The reference server is unseeded: combat draws come from the process-global
+``np.random.randint`` (server.py:562).  Parity therefore needs a *tape*: a
+pure function that returns the value of every combat draw from its position
+in the game.  The position visible at the reference call site (frame locals of
+``EvergladesGame.combat``) is (turn, node.ID, pid, gid, j); the tape is
+
+    r   = philox4x32_10(key=(seed_lo, seed_hi),
+                        ctr=(env, turn, node | pid<<8 | gid<<16 | (j>>2)<<24,
+                             DOMAIN | episode<<8))[j & 3]
+    uid = (r * n) >> 32                      # n = opposing alive units at the node
+
+Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
+(SC'11); constants below are the published ones and `philox4x32` is checked
+against the Random123 known-answer vectors in tests/test_tape.py.
+"""
+from __future__ import annotations
+
+M0 = 0xD2511F53
+M1 = 0xCD9E8D57
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = 0xFFFFFFFF
+
+DOMAIN_COMBAT = 0          # combat target draws (server.py:562)
+DOMAIN_AGENT_RANDOM = 1    # on-device random_actions agent
+
+
+def philox4x32(ctr, key, rounds: int = 10):
+    """Return the 4 x uint32 Philox block for a 4-word counter and 2-word key."""
+    c0, c1, c2, c3 = (int(x) & MASK for x in ctr)
+    k0, k1 = (int(x) & MASK for x in key)
+    for r in range(rounds):
+        if r:
+            k0 = (k0 + W0) & MASK
+            k1 = (k1 + W1) & MASK
+        p0 = M0 * c0
+        p1 = M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c3 ^ k1) & MASK, p0 & MASK
+    return c0, c1, c2, c3
+
+
+def combat_word(seed: int, env: int, turn: int, node: int, side: int, gid: int, j: int, episode: int = 0) -> int:
+    """The raw 32-bit tape word for the j-th alive attacker of (side, gid) at `node`."""
+    ctr = (env & MASK, turn & MASK, (node & 0xFF) | (side & 0xFF) << 8 | (gid & 0xFF) << 16 | ((j >> 2) & 0xFF) << 24,
+           DOMAIN_COMBAT | (episode & 0xFFFFFF) << 8)
+    key = (seed & MASK, (seed >> 32) & MASK)
+    return philox4x32(ctr, key)[j & 3]
+
+
+def combat_draw(seed: int, env: int, turn: int, node: int, side: int, gid: int, j: int, n: int, episode: int = 0) -> int:
+    """Value the patched ``np.random.randint(n)`` returns at server.py:562."""
+    return (combat_word(seed, env, turn, node, side, gid, j, episode) * int(n)) >> 32

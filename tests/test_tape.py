@@ -1,0 +1,51 @@
+"""The Philox tape: published known-answer vectors, and C oracle == Python harness."""
+import ctypes as C
+
+import numpy as np
+
+from oracle import tape, evg_oracle as eo
+
+# Random123 (Salmon et al., SC'11) kat_vectors for philox4x32-10
+KAT = [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def _c_philox(ctr, key):
+    c = np.array(ctr, dtype=np.uint32)
+    k = np.array(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    eo.lib().evo_philox(c.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+    return tuple(int(x) for x in o)
+
+
+def test_philox_known_answers_python():
+    for ctr, key, want in KAT:
+        assert tape.philox4x32(ctr, key) == want
+
+
+def test_philox_known_answers_c():
+    for ctr, key, want in KAT:
+        assert _c_philox(ctr, key) == want
+
+
+def test_c_matches_python_random_counters():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        ctr = tuple(int(x) for x in rng.integers(0, 2**32, 4))
+        key = tuple(int(x) for x in rng.integers(0, 2**32, 2))
+        assert _c_philox(ctr, key) == tape.philox4x32(ctr, key)
+
+
+def test_draw_is_in_range_and_uses_all_lanes():
+    seen = set()
+    for j in range(12):
+        w = tape.combat_word(7, 3, 10, 5, 1, 11, j)
+        seen.add(w)
+        for n in (1, 2, 13, 100):
+            assert 0 <= tape.combat_draw(7, 3, 10, 5, 1, 11, j, n) < n
+    assert len(seen) == 12
+    assert tape.combat_word(7, 3, 10, 5, 1, 11, 0, episode=1) != tape.combat_word(7, 3, 10, 5, 1, 11, 0)
