@@ -1,0 +1,413 @@
+// evg_capi.cu — host side of the C ABI declared in include/evgsim.h.
+// Validates the config, derives the device tables and launch geometry, and forwards every call to
+// the kernels of evg_kernels.cu.  Owns no device memory: all arrays are the caller's (evg_bind).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "evg_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(EVG_E_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct EvgSim {
+    EvgConfig cfg;
+    evg::Tables tables;
+    int64_t n_envs;
+    int device;
+    int grid;
+    size_t smem;
+    void* bound[EVG_BIND_COUNT];
+    bool is_bound;
+    int64_t launches;
+    int64_t steps;
+    EvgLayout layout;
+};
+
+namespace {
+
+// EvgConfig -> Tables.  Returns 0 or EVG_E_CONFIG with the reason in g_last_error.
+int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::Tables* out)
+{
+    evg::Tables t;
+    memset(&t, 0, sizeof(t));
+    if (c.abi_version != EVG_ABI_VERSION) return fail(EVG_E_CONFIG, "EvgConfig.abi_version %d != %d", c.abi_version, EVG_ABI_VERSION);
+    if (c.n_nodes < 2 || c.n_nodes > EVG_MAX_NODES) return fail(EVG_E_CONFIG, "n_nodes %d outside 2..%d", c.n_nodes, EVG_MAX_NODES);
+    if (c.n_unit_types < 1 || c.n_unit_types > EVG_MAX_UNIT_TYPES) return fail(EVG_E_CONFIG, "n_unit_types %d outside 1..%d", c.n_unit_types, EVG_MAX_UNIT_TYPES);
+    if (c.turn_limit < 1 || c.turn_limit > 65535) return fail(EVG_E_CONFIG, "turn_limit %d outside 1..65535", c.turn_limit);
+    if (c.capture_bonus < 0 || c.capture_bonus > 1000000) return fail(EVG_E_CONFIG, "capture_bonus %d outside 0..1e6", c.capture_bonus);
+    if (c.max_score < 1) return fail(EVG_E_CONFIG, "max_score %d must be positive", c.max_score);
+    if (c.auto_reset < EVG_AUTORESET_OFF || c.auto_reset > EVG_AUTORESET_NEXT) return fail(EVG_E_CONFIG, "auto_reset %d unknown", c.auto_reset);
+    t.n_nodes = c.n_nodes;
+    t.obs_len = 1 + 4 * c.n_nodes + 5 * EVG_NUM_GROUPS;
+    t.turn_limit = c.turn_limit;
+    t.capture_bonus = c.capture_bonus;
+    t.auto_reset = c.auto_reset;
+    t.max_score = (double)c.max_score;
+    t.seed_lo = (uint32_t)seed;
+    t.seed_hi = (uint32_t)(seed >> 32);
+    t.env_base = (uint32_t)env_id_offset;
+
+    int start[EVG_NUM_PLAYERS] = {-1, -1};
+    if (c.p1_node_map[0] != 0) return fail(EVG_E_CONFIG, "p1_node_map[0] must be 0");
+    for (int n = 1; n <= c.n_nodes; ++n) {
+        if (c.node_control_points[n] < 1 || c.node_control_points[n] > 32767) return fail(EVG_E_CONFIG, "node %d ControlPoints %d outside 1..32767", n, c.node_control_points[n]);
+        if (!(c.node_defense[n] >= 0.0) || c.node_defense[n] > 1e6) return fail(EVG_E_CONFIG, "node %d StructureDefense %g invalid", n, c.node_defense[n]);
+        const int ts = c.node_team_start[n];
+        if (ts < -1 || ts > 1) return fail(EVG_E_CONFIG, "node %d TeamStart %d outside -1..1", n, ts);
+        if (ts >= 0) start[ts] = n;  // team_starts[teamStart] = ID, last one wins (server.py:67-68)
+        const int m = c.p1_node_map[n];
+        if (m < 1 || m > c.n_nodes || c.p1_node_map[m] != n) return fail(EVG_E_CONFIG, "p1_node_map is not an involution at node %d", n);
+        t.node_cp[n] = (int16_t)c.node_control_points[n];
+        t.node_def[n] = c.node_defense[n];
+        t.node_team_start[n] = (int8_t)ts;
+        t.node_flags[n] = (uint8_t)((c.node_has_defense[n] ? 1 : 0) | (c.node_has_observe[n] ? 2 : 0) | (c.node_has_defend[n] ? 4 : 0));
+        t.p1_map[n] = (uint8_t)m;
+        for (int b = 1; b <= c.n_nodes; ++b) t.edge[n][b] = c.edge_distance[n][b];
+    }
+    for (int p = 0; p < EVG_NUM_PLAYERS; ++p)
+        if (start[p] < 0) return fail(EVG_E_CONFIG, "no node has TeamStart == %d", p);
+    for (int k = 0; k < c.n_unit_types; ++k) {
+        if (!(c.unit_armor[k] > 0.0) || c.unit_armor[k] > 1e6) return fail(EVG_E_CONFIG, "unit type %d Health %g must be in (0, 1e6]", k, c.unit_armor[k]);
+        if (c.unit_damage[k] < 0 || c.unit_damage[k] > 255 || c.unit_speed[k] < 0 || c.unit_speed[k] > 255 || c.unit_control[k] < 0 ||
+            c.unit_control[k] > 63 || c.unit_cost[k] < 0 || c.unit_cost[k] > 255)
+            return fail(EVG_E_CONFIG, "unit type %d: Damage/Speed/Cost must be 0..255 and Control 0..63", k);
+        t.unit_armor[k] = c.unit_armor[k];
+        t.ut_damage[k] = (uint8_t)c.unit_damage[k];
+        t.ut_speed[k] = (uint8_t)c.unit_speed[k];
+        t.ut_control[k] = (uint8_t)c.unit_control[k];
+        t.ut_cost[k] = (uint8_t)c.unit_cost[k];
+    }
+    int max_units = 0, max_size = 0, small = 0, per_player_slots = 0;
+    for (int p = 0; p < EVG_NUM_PLAYERS; ++p) {
+        int slots = 0, units = 0;
+        for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
+            const int L = p * EVG_NUM_GROUPS + g, size = c.group_size[p][g], type = c.group_type[p][g];
+            if (size < 1 || size > EVG_MAX_GROUP_UNITS) return fail(EVG_E_CONFIG, "group %d of player %d has %d units; supported 1..%d", g, p, size, EVG_MAX_GROUP_UNITS);
+            if (type >= c.n_unit_types) return fail(EVG_E_CONFIG, "group %d of player %d has unknown unit type %d", g, p, type);
+            t.g_type[L] = (uint8_t)type;
+            t.g_size[L] = (uint8_t)size;
+            t.g_slot[L] = (uint16_t)slots;  // per-player offset for now
+            slots += round_up(size, 4);     // every group starts on a 32-byte sector
+            units += size;
+            if (size > max_size) max_size = size;
+            if (size < 8) small = 1;
+            t.init_w0[L] = (uint32_t)start[p] | 100u << evg::W0_AVG_SHIFT;  // health 100.0 each (definitions.py:62)
+            t.init_w1[L] = (1u << size) - 1u;                               // all alive, arrival turn 0 (listed in gid order)
+        }
+        if (slots > per_player_slots) per_player_slots = slots;
+        if (units > max_units) max_units = units;
+    }
+    for (int g = 0; g < EVG_NUM_GROUPS; ++g) t.g_slot[EVG_NUM_GROUPS + g] = (uint16_t)(t.g_slot[EVG_NUM_GROUPS + g] + per_player_slots);
+    t.health_slots = 2 * per_player_slots;
+    t.max_group_size = max_size;
+    t.has_small_groups = small;
+    t.hist_words = (max_units + 1) / 2 + 1;
+    // node state after game_init's capture() at turn 0 (server.py:206,744-745,763-765)
+    for (int n = 1; n <= c.n_nodes; ++n) {
+        int cs = 0, cb = c.node_team_start[n];
+        for (int p = 0; p < EVG_NUM_PLAYERS; ++p)
+            if (start[p] == n) {
+                cs = p == 0 ? c.node_control_points[n] : -c.node_control_points[n];
+                cb = p;
+            }
+        t.init_node[n] = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
+    }
+    // resident record: 48 group words + turn + episode + n_nodes node words, padded to 32 bytes
+    const int rec_bytes = round_up((evg::kRecNode0 + c.n_nodes) * 4, 32);
+    t.rec_words8 = rec_bytes / 8;
+    // per-warp shared-memory carve-up
+    const int nn = c.n_nodes + 1;
+    t.sm_acc = round_up(rec_bytes, 16);
+    t.sm_hist = t.sm_acc + round_up(2 * nn * 4, 16);
+    t.sm_obs = t.sm_hist + round_up(2 * t.hist_words * 4, 16);
+    t.sm_misc = t.sm_obs + round_up(2 * t.obs_len * 4, 16);
+    t.sm_warp_stride = t.sm_misc + round_up(256 + 2 * nn, 16);
+    t.sm_tables_bytes = round_up((int)sizeof(evg::Tables), 16);
+    *out = t;
+    return EVG_OK;
+}
+
+int check_sim(const EvgSim* s, bool need_bound)
+{
+    if (!s) return fail(EVG_E_ARG, "null EvgSim handle");
+    if (need_bound && !s->is_bound) return fail(EVG_E_STATE, "evg_bind() must be called before this entry point");
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return EVG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int evg_abi_version(void) { return EVG_ABI_VERSION; }
+
+const char* evg_last_error(void) { return g_last_error.c_str(); }
+
+int evg_default_config(EvgConfig* cfg)
+{
+    if (!cfg) return fail(EVG_E_ARG, "null config");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = EVG_ABI_VERSION;
+    cfg->n_nodes = 11;
+    cfg->n_unit_types = 3;
+    cfg->turn_limit = 150;     // server.py:321
+    cfg->capture_bonus = 1000; // server.py:304
+    cfg->max_score = 3700;     // env.py:11
+    cfg->auto_reset = EVG_AUTORESET_OFF;
+    // DemoMap.json: node -> (neighbour, distance)...
+    static const int edges[18][3] = {{1, 2, 6}, {1, 4, 6}, {2, 3, 4}, {2, 5, 4}, {3, 4, 4}, {3, 5, 6}, {3, 6, 3}, {3, 7, 6}, {4, 7, 4},
+                                     {5, 8, 4}, {5, 9, 6}, {6, 9, 3}, {7, 9, 6}, {7, 10, 4}, {8, 9, 4}, {8, 11, 6}, {9, 10, 4}, {10, 11, 6}};
+    for (const auto& e : edges) {
+        cfg->edge_distance[e[0]][e[1]] = (uint8_t)e[2];
+        cfg->edge_distance[e[1]][e[0]] = (uint8_t)e[2];
+    }
+    static const double defense[12] = {0, 1, 1.5, 1.75, 1.5, 1.75, 1.75, 1.75, 1.5, 1.75, 1.5, 1};
+    static const uint8_t p1map[12] = {0, 11, 8, 9, 10, 5, 6, 7, 2, 3, 4, 1};  // server.py:89
+    for (int n = 0; n <= EVG_MAX_NODES; ++n) cfg->node_team_start[n] = -1;
+    for (int n = 1; n <= 11; ++n) {
+        cfg->node_control_points[n] = (n == 1 || n == 11) ? 500 : 100;
+        cfg->node_defense[n] = defense[n];
+        cfg->p1_node_map[n] = p1map[n];
+    }
+    cfg->node_team_start[1] = 0;
+    cfg->node_team_start[11] = 1;
+    cfg->node_has_observe[2] = cfg->node_has_observe[8] = 1;
+    cfg->node_has_defense[4] = cfg->node_has_defense[10] = 1;
+    // UnitDefinitions.json: tank, controller, striker
+    static const double armor[3] = {3, 2, 1};
+    static const int damage[3] = {1, 1, 2}, speed[3] = {1, 1, 2}, control[3] = {1, 2, 1};
+    for (int k = 0; k < 3; ++k) {
+        cfg->unit_armor[k] = armor[k];
+        cfg->unit_damage[k] = damage[k];
+        cfg->unit_speed[k] = speed[k];
+        cfg->unit_control[k] = control[k];
+        cfg->unit_cost[k] = 1;
+    }
+    // env.py:145-156: classes cycle controller, striker, tank; 8 units each, the last group 12
+    static const uint8_t cycle[3] = {1, 2, 0};
+    for (int p = 0; p < EVG_NUM_PLAYERS; ++p)
+        for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
+            cfg->group_type[p][g] = cycle[g % 3];
+            cfg->group_size[p][g] = g == EVG_NUM_GROUPS - 1 ? 12 : 8;
+        }
+    return EVG_OK;
+}
+
+int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_id_offset, int device, EvgSim** out)
+{
+    if (!cfg || !out) return fail(EVG_E_ARG, "null argument");
+    *out = nullptr;
+    if (n_envs < 1 || n_envs > (int64_t)1 << 31) return fail(EVG_E_ARG, "n_envs %lld outside 1..2^31", (long long)n_envs);
+    if (env_id_offset < 0 || env_id_offset + n_envs > (int64_t)1 << 32) return fail(EVG_E_ARG, "global match ids must fit 32 bits");
+    evg::Tables t;
+    int rc = build_tables(*cfg, seed, env_id_offset, &t);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) return fail(EVG_E_CUDA, "no CUDA device available (%s); libevgsim has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(EVG_E_ARG, "device %d outside 0..%d", device, ndev - 1);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    EvgSim* s = new (std::nothrow) EvgSim();
+    if (!s) return fail(EVG_E_ARG, "out of host memory");
+    s->cfg = *cfg;
+    s->tables = t;
+    s->n_envs = n_envs;
+    s->device = device;
+    s->is_bound = false;
+    s->launches = 0;
+    s->steps = 0;
+    s->smem = (size_t)t.sm_tables_bytes + 128 + (size_t)evg::kWarpsPerBlock * t.sm_warp_stride;
+    if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
+    int per_sm = 0;
+    if ((e = evg::step_occupancy(s->smem, &per_sm)) != cudaSuccess || per_sm < 1) { delete s; return cuda_fail(e, "occupancy query"); }
+    // persistent CTAs: a whole number of resident waves, never more CTAs than matches need
+    const int64_t need = (n_envs + evg::kWarpsPerBlock - 1) / evg::kWarpsPerBlock;
+    const int64_t resident = (int64_t)prop.multiProcessorCount * per_sm;
+    s->grid = (int)(need < resident ? need : resident);
+    EvgLayout& L = s->layout;
+    L.n_envs = n_envs;
+    L.obs_len = t.obs_len;
+    L.record_bytes = t.rec_words8 * 8;
+    L.health_slots = t.health_slots;
+    L.action_bytes = 2 * EVG_MAX_ACTIONS * 2;
+    L.records_bytes = n_envs * L.record_bytes;
+    L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
+    L.stats_bytes = evg::ST_COUNT * 8;
+    *out = s;
+    return EVG_OK;
+}
+
+int evg_destroy(EvgSim* sim)
+{
+    if (!sim) return fail(EVG_E_ARG, "null EvgSim handle");
+    delete sim;
+    return EVG_OK;
+}
+
+int evg_layout(const EvgSim* sim, EvgLayout* out)
+{
+    if (!sim || !out) return fail(EVG_E_ARG, "null argument");
+    *out = sim->layout;
+    return EVG_OK;
+}
+
+int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
+{
+    if (!sim || !device_ptrs) return fail(EVG_E_ARG, "null argument");
+    if (n_ptrs != EVG_BIND_COUNT) return fail(EVG_E_ARG, "evg_bind expects %d pointers, got %d", EVG_BIND_COUNT, n_ptrs);
+    for (int i = 0; i < EVG_BIND_COUNT; ++i) {
+        if (!device_ptrs[i]) return fail(EVG_E_ARG, "bind slot %d is null", i);
+        if ((uintptr_t)device_ptrs[i] % 16) return fail(EVG_E_ARG, "bind slot %d is not 16-byte aligned", i);
+        sim->bound[i] = device_ptrs[i];
+    }
+    sim->is_bound = true;
+    return EVG_OK;
+}
+
+int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (!d_mask) {
+        if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_STATS], 0, evg::ST_COUNT * 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(stats)");
+        sim->steps = 0;
+    }
+    e = evg::launch_reset(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], d_mask, d_obs,
+                          sim->n_envs, sim->grid, sim->smem, st);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_reset_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
+int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_status,
+             int32_t* d_scores, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_actions || !d_obs || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step: actions/obs/reward/done must be non-null");
+    evg::StepArgs a;
+    a.records = (uint32_t*)sim->bound[EVG_BIND_RECORDS];
+    a.health = (double*)sim->bound[EVG_BIND_HEALTH];
+    a.stats = (unsigned long long*)sim->bound[EVG_BIND_STATS];
+    a.actions = d_actions;
+    a.obs = d_obs;
+    a.reward = d_reward;
+    a.done = d_done;
+    a.status = d_status;
+    a.scores = d_scores;
+    a.n_envs = sim->n_envs;
+    cudaError_t e = evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_step_kernel launch");
+    sim->launches += 1;
+    sim->steps += 1;
+    return EVG_OK;
+}
+
+int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done, int8_t* d_actions,
+                  float* d_obs, float* d_reward, uint8_t* d_done, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!h_actions || !h_obs || !h_reward || !h_done) return fail(EVG_E_ARG, "evg_step_host: host buffers must be non-null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = sim->n_envs;
+    cudaError_t e = cudaMemcpyAsync(d_actions, h_actions, (size_t)n * sim->layout.action_bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D actions");
+    rc = evg_step(sim, d_actions, d_obs, d_reward, d_done, nullptr, nullptr, stream);
+    if (rc) return rc;
+    if ((e = cudaMemcpyAsync(h_obs, d_obs, (size_t)n * 2 * sim->layout.obs_len * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H obs");
+    if ((e = cudaMemcpyAsync(h_reward, d_reward, (size_t)n * 2 * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H reward");
+    if ((e = cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H done");
+    return EVG_OK;
+}
+
+int evg_export_state(EvgSim* sim, int64_t first, int64_t count, EvgEnvState* d_states, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_states || first < 0 || count < 0 || first + count > sim->n_envs) return fail(EVG_E_ARG, "evg_export_state: bad range [%lld,+%lld)", (long long)first, (long long)count);
+    cudaError_t e = evg::launch_export(sim->tables, (const uint32_t*)sim->bound[EVG_BIND_RECORDS], (const double*)sim->bound[EVG_BIND_HEALTH],
+                                       first, count, d_states, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_export_kernel launch");
+    sim->launches += count > 0;
+    return EVG_OK;
+}
+
+int evg_import_state(EvgSim* sim, int64_t first, int64_t count, const EvgEnvState* d_states, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_states || first < 0 || count < 0 || first + count > sim->n_envs) return fail(EVG_E_ARG, "evg_import_state: bad range [%lld,+%lld)", (long long)first, (long long)count);
+    cudaError_t e = evg::launch_import(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], first, count,
+                                       d_states, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_import_kernel launch");
+    sim->launches += count > 0;
+    return EVG_OK;
+}
+
+int evg_episode_stats(EvgSim* sim, EvgEpisodeStats* host_out, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!host_out) return fail(EVG_E_ARG, "null output");
+    unsigned long long h[evg::ST_COUNT];
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(h, sim->bound[EVG_BIND_STATS], sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H stats");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    host_out->episodes = (int64_t)h[evg::ST_EPISODES];
+    host_out->wins[0] = (int64_t)h[evg::ST_WIN0];
+    host_out->wins[1] = (int64_t)h[evg::ST_WIN1];
+    host_out->ties = (int64_t)h[evg::ST_TIES];
+    host_out->total_turns = (int64_t)h[evg::ST_TURNS];
+    host_out->total_score[0] = (int64_t)h[evg::ST_SCORE0];
+    host_out->total_score[1] = (int64_t)h[evg::ST_SCORE1];
+    for (int k = 0; k < 4; ++k) host_out->status_count[k] = (int64_t)h[evg::ST_STATUS0 + k];
+    host_out->env_turns = sim->steps * sim->n_envs;
+    return EVG_OK;
+}
+
+int evg_agent_random(EvgSim* sim, int8_t* d_actions, int32_t player, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_actions || player < -1 || player > 1) return fail(EVG_E_ARG, "evg_agent_random: bad argument");
+    cudaError_t e = evg::launch_agent_random(sim->tables, (const uint32_t*)sim->bound[EVG_BIND_RECORDS], d_actions, player, sim->n_envs,
+                                             (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_agent_random_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
+int64_t evg_launch_count(const EvgSim* sim) { return sim ? sim->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// evg_internal.h — device tables, resident record layout and launcher prototypes shared by
+// evg_kernels.cu (sm_100a kernels) and evg_capi.cu (the C ABI of include/evgsim.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/evgsim.h"
+
+namespace evg {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kGroupLanes = EVG_NUM_PLAYERS * EVG_NUM_GROUPS;  // 24: lane = side*12 + gid
+constexpr int kNN = EVG_MAX_NODES + 1;
+
+// ---------------------------------------------------------------------------------------------
+// Resident per-match record, 32-bit words, little endian:
+//   [0..47]   24 group records, 2 words each (lane L owns words 2L, 2L+1)
+//       w0: loc[0:6) dest[6:12) dist[12:20) ready[20] moving[21] avg_health[24:31)
+//       w1: alive unit mask[0:16) arrival turn[16:32)
+//   [48]      turn            [49] episode
+//   [50+i]    node i+1: controlState int16 | controlledBy int8 << 16
+// padded to a multiple of 32 bytes (DemoMap: 61 words -> 256 B = one 8-byte load per lane).
+// Unit health lives apart: double[health_slots] per match, group (side,g) at slot g_slot[L].
+// ---------------------------------------------------------------------------------------------
+constexpr int kRecGroupWords = 2 * kGroupLanes;  // 48
+constexpr int kRecTurn = 48;
+constexpr int kRecEpisode = 49;
+constexpr int kRecNode0 = 50;
+
+constexpr uint32_t W0_LOC_MASK = 0x3Fu;
+constexpr int W0_DEST_SHIFT = 6;
+constexpr int W0_DIST_SHIFT = 12;
+constexpr uint32_t W0_READY = 1u << 20;
+constexpr uint32_t W0_MOVING = 1u << 21;
+constexpr int W0_AVG_SHIFT = 24;
+
+// Static tables, passed to every kernel by value (__grid_constant__) and staged in shared memory.
+struct Tables {
+    int32_t n_nodes, obs_len, rec_words8, health_slots;
+    int32_t turn_limit, capture_bonus, auto_reset, max_group_size;
+    int32_t has_small_groups, hist_words, pad0, pad1;  // hist_words: u32 words per side of the damage histogram
+    uint32_t seed_lo, seed_hi, env_base, pad2;
+    double max_score;
+    // per-warp shared-memory carve-up (bytes)
+    int32_t sm_acc, sm_hist, sm_obs, sm_misc, sm_warp_stride, sm_tables_bytes, pad3, pad4;
+    double node_def[kNN];
+    double unit_armor[EVG_MAX_UNIT_TYPES];
+    uint32_t init_w0[kGroupLanes], init_w1[kGroupLanes];
+    uint32_t init_node[kNN];
+    int16_t node_cp[kNN];
+    uint16_t g_slot[kGroupLanes];
+    int8_t node_team_start[kNN];
+    uint8_t node_flags[kNN];  // bit0 'DEFENSE' (obs), bit1 'OBSERVE' (obs), bit2 'DEFEND' (combat bonus)
+    uint8_t p1_map[kNN];
+    uint8_t ut_damage[EVG_MAX_UNIT_TYPES], ut_speed[EVG_MAX_UNIT_TYPES], ut_control[EVG_MAX_UNIT_TYPES],
+        ut_cost[EVG_MAX_UNIT_TYPES];
+    uint8_t g_type[kGroupLanes], g_size[kGroupLanes];
+    uint8_t edge[kNN][kNN];
+};
+
+// device statistics accumulators (uint64 each); matches EvgEpisodeStats minus env_turns
+enum { ST_EPISODES = 0, ST_WIN0, ST_WIN1, ST_TIES, ST_TURNS, ST_SCORE0, ST_SCORE1, ST_STATUS0, ST_COUNT = ST_STATUS0 + 4 };
+
+struct StepArgs {
+    uint32_t* records;
+    double* health;
+    unsigned long long* stats;
+    const int8_t* actions;
+    float* obs;
+    float* reward;
+    uint8_t* done;
+    uint8_t* status;
+    int32_t* scores;
+    int64_t n_envs;
+};
+
+// launchers (evg_kernels.cu); all asynchronous on `stream`, return the launch error
+cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, float* obs,
+                         int64_t n_envs, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_export(const Tables& t, const uint32_t* records, const double* health, int64_t first, int64_t count,
+                          EvgEnvState* out, cudaStream_t stream);
+cudaError_t launch_import(const Tables& t, uint32_t* records, double* health, int64_t first, int64_t count,
+                          const EvgEnvState* in, cudaStream_t stream);
+cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t* actions, int player, int64_t n_envs,
+                                cudaStream_t stream);
+cudaError_t step_occupancy(size_t smem, int* blocks_per_sm);
+cudaError_t set_step_smem(size_t smem);
+
+}  // namespace evg

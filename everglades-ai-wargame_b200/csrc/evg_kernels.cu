@@ -1,0 +1,690 @@
+// evg_kernels.cu — hand-written sm_100a kernels of the batched Everglades turn step.
+//
+// Mapping: ONE WARP PER MATCH.  Lanes change role with the phase of the turn:
+//   lane L < 24  <->  group (side = L/12, gid = L%12)     action decode, movement, scoring
+//   lane n-1     <->  node n                               capture, scoring, board observation
+//   half-warp u  <->  unit slot u of one target group      combat damage + fp64 health update
+//   lane p       <->  (attacking group, block of 4 units)  Philox draws
+// Static tables (map adjacency, unit definitions, loadout) are staged in shared memory once per
+// CTA; a CTA is persistent (grid-stride over matches).  The resident record of a match is one
+// 256-byte line (DemoMap) read/written with one 8-byte access per lane; observations are staged
+// in shared memory and streamed out as contiguous float2 rows.  No tensor cores: the path is
+// byte/integer work plus a handful of IEEE fp64 operations that decide unit deaths.
+//
+// Reference semantics (file:line) are cited per phase; the reference is
+//   server.py = everglades-server/everglades_server/server.py
+//   env.py    = gym-everglades/gym_everglades/envs/everglades_env.py
+// and the CPU oracle that checks this file is oracle/evg_oracle.c.
+#include "evg_internal.h"
+
+namespace evg {
+
+#define FULL 0xFFFFFFFFu
+
+struct WarpSmem {
+    uint32_t* rec;   // resident record, rec_words8*2 words
+    uint32_t* acc;   // [2][nn] per (side,node) accumulators
+    uint32_t* hist;  // [2][hist_words] damage histogram, 2 x u16 per word
+    float* obs;      // [2][obs_len] observation staging
+    uint32_t* res;   // [24] combat result per group: alive mask | avg_health << 16
+    uint16_t* act;   // [14] action rows (gid | nid << 8)
+    uint8_t* pair;   // [96] (lane | block << 5) draw work list
+    uint8_t* tb;     // [24] histogram base of each fighting group
+    uint8_t* nb;     // [2][nn] histogram base of each (side,node)
+};
+
+__device__ __forceinline__ WarpSmem carve(unsigned char* base, const Tables& S)
+{
+    WarpSmem W;
+    W.rec = reinterpret_cast<uint32_t*>(base);
+    W.acc = reinterpret_cast<uint32_t*>(base + S.sm_acc);
+    W.hist = reinterpret_cast<uint32_t*>(base + S.sm_hist);
+    W.obs = reinterpret_cast<float*>(base + S.sm_obs);
+    unsigned char* m = base + S.sm_misc;
+    W.res = reinterpret_cast<uint32_t*>(m);
+    W.act = reinterpret_cast<uint16_t*>(m + 96);
+    W.pair = m + 128;
+    W.tb = m + 224;
+    W.nb = m + 256;
+    return W;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); same function as oracle/tape.py, oracle/evg_oracle.c.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                               uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        if (r) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Per-(side,node) sums over the groups LISTED at the node (node.groups[pid]: location == node and
+// not destroyed).  One shared-memory atomic per group packs three reductions:
+//   [0:10)  units of all listed groups, moving or not   (board_state opponent count, server.py:446-449)
+//   [10:24) sum count*control of non-moving groups       (capture points, server.py:718-724)
+//   [24:29) number of non-moving groups                  (controllers, server.py:725-726)
+__device__ __forceinline__ void node_accumulate(const Tables& S, const WarpSmem& W, int lane, bool is_grp, int side,
+                                                uint32_t w0, uint32_t w1, int nn)
+{
+    for (int i = lane; i < 2 * nn; i += 32) W.acc[i] = 0;
+    __syncwarp();
+    const uint32_t alive = w1 & 0xFFFFu;
+    if (is_grp && alive) {
+        const uint32_t cnt = __popc(alive);
+        uint32_t v = cnt;
+        if (!(w0 & W0_MOVING)) v |= (cnt * S.ut_control[S.g_type[lane]]) << 10 | 1u << 24;
+        atomicAdd(&W.acc[side * nn + (w0 & W0_LOC_MASK)], v);
+    }
+    __syncwarp();
+}
+
+// board_state (server.py:382-455) + player_state (server.py:457-501) + concat (env.py:158-171)
+// for both players, staged in shared memory and streamed out as one contiguous row.
+__device__ __forceinline__ void pack_obs(const Tables& S, const WarpSmem& W, int lane, bool is_grp, int side, int gid,
+                                         uint32_t w0, uint32_t w1, uint32_t nw, uint32_t turn, int nn, float* out)
+{
+    const int L = S.obs_len;
+    if (lane == 0) {
+        W.obs[0] = (float)turn;
+        W.obs[L] = (float)turn;
+    }
+    if (lane < S.n_nodes) {
+        const int n = lane + 1;
+        const uint32_t f = S.node_flags[n];
+        const float fd = (float)(f & 1u), fo = (float)((f >> 1) & 1u);
+        const float cs = (float)(int)(int16_t)(nw & 0xFFFFu);  // raw sign for both viewers
+        float* o0 = W.obs + 1 + 4 * lane;                      // player 0: slot k shows node k+1
+        o0[0] = fd; o0[1] = fo; o0[2] = cs; o0[3] = (float)(W.acc[nn + n] & 1023u);
+        float* o1 = W.obs + L + 1 + 4 * ((int)S.p1_map[n] - 1);  // player 1: node n sits in slot p1_map[n] (involution)
+        o1[0] = fd; o1[1] = fo; o1[2] = cs; o1[3] = (float)(W.acc[n] & 1023u);
+    }
+    if (is_grp) {
+        float* o = W.obs + side * L + 1 + 4 * S.n_nodes + 5 * gid;
+        const uint32_t loc = w0 & W0_LOC_MASK;
+        o[0] = (float)(side ? (uint32_t)S.p1_map[loc] : loc);
+        o[1] = (float)S.g_type[lane];
+        o[2] = (float)((w0 >> W0_AVG_SHIFT) & 127u);
+        o[3] = (float)((w0 >> 21) & 1u);
+        o[4] = (float)__popc(w1 & 0xFFFFu);
+    }
+    __syncwarp();
+    float2* o2 = reinterpret_cast<float2*>(out);  // 2*obs_len floats per match: always 8-byte aligned
+    const float2* s2 = reinterpret_cast<const float2*>(W.obs);
+    for (int i = lane; i < L; i += 32) __stcs(o2 + i, s2[i]);
+    __syncwarp();
+}
+
+// numpy's float64 pairwise sum (np.sum at server.py:481) of the `size` unit slots held one per lane
+// in a 16-lane half-warp (slots >= size and dead units hold 0.0, which adds exactly).
+__device__ __forceinline__ double half_pairwise_sum(const Tables& S, double h, int size, int u, int half)
+{
+    double v = h;
+    const double up = __shfl_down_sync(FULL, h, 8, 16);
+    if (size == 16) v = __dadd_rn(h, up);  // n == 16: r[k] = a[k] + a[8+k] before the tree
+    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1, 16));
+    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2, 16));
+    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 4, 16));
+    double res = v;  // lanes 0..7: ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7))
+    for (int i = 8; i < S.max_group_size && i < 16; ++i) {
+        const double x = __shfl_sync(FULL, h, i, 16);
+        if (size < 16 && i < size) res = __dadd_rn(res, x);  // remainder added sequentially
+    }
+    if (S.has_small_groups) {  // n < 8: plain left-to-right loop from 0.0
+        double seq = 0.0;
+        for (int i = 0; i < 7; ++i) {
+            const double x = __shfl_sync(FULL, h, i, 16);
+            if (i < size) seq = __dadd_rn(seq, x);
+        }
+        if (size < 8) res = seq;
+    }
+    (void)u; (void)half;
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One turn of one match by one warp: env.py:32-73 step -> server.py:211-279 game_turn.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, const StepArgs& A, int64_t env, int lane,
+                                           unsigned long long* cta_stats)
+{
+    const int nn = S.n_nodes + 1;
+    const bool is_grp = lane < kGroupLanes;
+    const int side = lane >= EVG_NUM_GROUPS ? 1 : 0;
+    const int gid = lane - side * EVG_NUM_GROUPS;
+
+    // ---- load the resident record (coalesced 8-byte per lane) and this turn's action rows
+    uint2* grec = reinterpret_cast<uint2*>(A.records) + env * S.rec_words8;
+    uint2* srec2 = reinterpret_cast<uint2*>(W.rec);
+    for (int i = lane; i < S.rec_words8; i += 32) srec2[i] = grec[i];
+    if (lane < 2 * EVG_MAX_ACTIONS)
+        W.act[lane] = reinterpret_cast<const uint16_t*>(A.actions)[env * (2 * EVG_MAX_ACTIONS) + lane];
+    __syncwarp();
+    uint32_t w0 = is_grp ? W.rec[2 * lane] : 0u, w1 = is_grp ? W.rec[2 * lane + 1] : 0u;
+    uint32_t nw = lane < S.n_nodes ? W.rec[kRecNode0 + lane] : 0u;
+    uint32_t turn = W.rec[kRecTurn] + 1u;  // server.py:214
+    uint32_t episode = W.rec[kRecEpisode];
+    const int gtype = is_grp ? S.g_type[lane] : 0;
+
+    // ---- action decode + validation, server.py:218-271.  Each group lane scans its player's 7 rows
+    // and takes the first that names it and passes (t2) not moving, (t3) destination adjacent; a
+    // row that fails does not consume the group's one command per turn (t1 only sees accepted rows).
+    if (is_grp && !(w0 & W0_MOVING)) {
+        const uint32_t loc = w0 & W0_LOC_MASK;
+        bool taken = false;
+#pragma unroll
+        for (int i = 0; i < EVG_MAX_ACTIONS; ++i) {
+            const uint32_t a = W.act[side * EVG_MAX_ACTIONS + i];
+            const int ag = (int)(int8_t)(a & 0xFFu);
+            int an = (int)(int8_t)(a >> 8);
+            if (!taken && ag == gid) {
+                an = (an >= 0 && an <= S.n_nodes) ? an : 0;
+                if (side) an = S.p1_map[an];  // server.py:233-234
+                const uint32_t d = S.edge[loc][an];
+                if (d) {  // server.py:267-270
+                    taken = true;
+                    w0 = (w0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | (uint32_t)an << W0_DEST_SHIFT |
+                         d << W0_DIST_SHIFT | W0_READY;
+                }
+            }
+        }
+    }
+
+    // ---- combat, server.py:503-654
+    {
+        const uint32_t alive = w1 & 0xFFFFu;
+        const uint32_t cnt = __popc(alive);
+        const uint32_t loc = w0 & W0_LOC_MASK;
+        const bool present = is_grp && alive && !(w0 & W0_MOVING);  // listed and not in transit (:523-530)
+        for (int i = lane; i < 2 * nn; i += 32) W.acc[i] = 0;
+        __syncwarp();
+        if (present) atomicAdd(&W.acc[side * nn + loc], cnt);  // counts[player] summed per node
+        __syncwarp();
+        const bool fighting = present && W.acc[(1 - side) * nn + loc] != 0;  // both players present (:539)
+        const uint32_t fmask = __ballot_sync(FULL, fighting);
+        if (fmask) {
+            // Histogram slot of a target = (position of its group among the side's fighting groups
+            // ordered by node, then node-list order) + alive rank in the group.  Within one node that
+            // is exactly the uid the reference draws (uid -> (group, r-th unit alive
+            // before combat) is fixed before any damage lands).
+            const uint32_t arrival = w1 >> 16;
+            const uint32_t key = (uint32_t)side << 31 | loc << 25 | arrival << 9 | (uint32_t)gid << 5 | cnt;
+            uint32_t tbase = 0;
+            bool first = true;
+            for (uint32_t m = fmask; m; m &= m - 1) {
+                const uint32_t ok = __shfl_sync(FULL, key, __ffs(m) - 1);
+                if (((ok ^ key) >> 31) == 0 && ok < key) {
+                    tbase += ok & 31u;
+                    if (((ok ^ key) >> 25) == 0) first = false;
+                }
+            }
+            for (int i = lane; i < 2 * S.hist_words; i += 32) W.hist[i] = 0;
+            if (fighting) {
+                W.tb[lane] = (uint8_t)tbase;
+                if (first) W.nb[side * nn + loc] = (uint8_t)tbase;
+            }
+            // work list of (group, block of 4 attackers)
+            const uint32_t nblk = fighting ? (cnt + 3) >> 2 : 0;
+            const uint32_t b1 = __ballot_sync(FULL, nblk >= 1), b2 = __ballot_sync(FULL, nblk >= 2),
+                           b3 = __ballot_sync(FULL, nblk >= 3), b4 = __ballot_sync(FULL, nblk >= 4);
+            const uint32_t lt = (1u << lane) - 1u;
+            const int o1 = __popc(b1), o2 = o1 + __popc(b2), o3 = o2 + __popc(b3), npairs = o3 + __popc(b4);
+            if (nblk >= 1) W.pair[__popc(b1 & lt)] = (uint8_t)lane;
+            if (nblk >= 2) W.pair[o1 + __popc(b2 & lt)] = (uint8_t)(lane | 1 << 5);
+            if (nblk >= 3) W.pair[o2 + __popc(b3 & lt)] = (uint8_t)(lane | 2 << 5);
+            if (nblk >= 4) W.pair[o3 + __popc(b4 & lt)] = (uint8_t)(lane | 3 << 5);
+            __syncwarp();
+            // draws: every alive unit of a fighting group targets uid = randint(opposing alive units
+            // at the node) and adds its type's damage to infliction[uid], server.py:549-566
+            for (int base = 0; base < npairs; base += 32) {
+                const int p = base + lane;
+                if (p < npairs) {
+                    const uint32_t pr = W.pair[p];
+                    const int L = pr & 31, k = pr >> 5;
+                    const int gs = L >= EVG_NUM_GROUPS ? 1 : 0, gg = L - gs * EVG_NUM_GROUPS;
+                    const uint32_t gl = W.rec[2 * L] & W0_LOC_MASK;  // loc/alive untouched since the load
+                    const int gcnt = __popc(W.rec[2 * L + 1] & 0xFFFFu);
+                    const uint32_t n = W.acc[(1 - gs) * nn + gl];
+                    const uint32_t hb = W.nb[(1 - gs) * nn + gl];
+                    const uint32_t dmg = S.ut_damage[S.g_type[L]];
+                    uint32_t r[4];
+                    philox4x32_10(S.env_base + (uint32_t)env, turn, gl | (uint32_t)gs << 8 | (uint32_t)gg << 16 | (uint32_t)k << 24,
+                                  episode << 8, S.seed_lo, S.seed_hi, r);
+                    uint32_t* hist = W.hist + (1 - gs) * S.hist_words;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (4 * k + q < gcnt) {
+                            const uint32_t idx = hb + __umulhi(r[q], n);
+                            atomicAdd(&hist[idx >> 1], dmg << ((idx & 1u) * 16));
+                        }
+                }
+            }
+            __syncwarp();
+            // apply: two target groups per pass, one unit slot per lane of a half-warp; server.py:573-643
+            const int half = lane >> 4, u = lane & 15;
+            for (uint32_t m = fmask; m;) {
+                const int L0 = __ffs(m) - 1;
+                m &= m - 1;
+                const int L1 = m ? __ffs(m) - 1 : -1;
+                if (m) m &= m - 1;
+                const int L = half ? L1 : L0;
+                const bool act = L >= 0;
+                const int Ls = act ? L : 0;
+                const int gs = Ls >= EVG_NUM_GROUPS ? 1 : 0;
+                const uint32_t gw0 = W.rec[2 * Ls], gw1 = W.rec[2 * Ls + 1];
+                const uint32_t gl = gw0 & W0_LOC_MASK;
+                const uint32_t galive = act ? gw1 & 0xFFFFu : 0u;
+                const int gsize = S.g_size[Ls], gt = S.g_type[Ls];
+                const bool mine = (galive >> u) & 1u;
+                double* hp = A.health + env * S.health_slots + S.g_slot[Ls] + u;
+                double h = 0.0;
+                uint32_t d = 0;
+                if (mine) {
+                    const uint32_t idx = (uint32_t)W.tb[Ls] + __popc(galive & ((1u << u) - 1u));
+                    d = (W.hist[gs * S.hist_words + (idx >> 1)] >> ((idx & 1u) * 16)) & 0xFFFFu;
+                    h = *hp;
+                }
+                bool dead = false;
+                if (d) {
+                    // loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
+                    const uint32_t nwd = W.rec[kRecNode0 + gl - 1];
+                    const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
+                    const int bonus = (cb == gs ? 1 : 0) + ((S.node_flags[gl] >> 2) & 1);
+                    const double node_def = __dmul_rn((double)bonus, S.node_def[gl]);
+                    const double loss = __ddiv_rn(__dmul_rn(10.0, (double)d), __dadd_rn(S.unit_armor[gt], node_def));
+                    h = __dsub_rn(h, loss);  // server.py:609
+                    if (h <= 0.0) {          // server.py:615-618
+                        h = 0.0;
+                        dead = true;
+                    }
+                    *hp = h;
+                }
+                const uint32_t deadmask = (__ballot_sync(FULL, dead) >> (16 * half)) & 0xFFFFu;
+                const uint32_t nalive = galive & ~deadmask;
+                const double hsum = half_pairwise_sum(S, h, gsize, u, half);
+                if (act && u == 0) {
+                    // player_state's int((health*1.)/units_alive), server.py:491
+                    const int avg = nalive ? (int)__ddiv_rn(hsum, (double)__popc(nalive)) : 0;
+                    W.res[Ls] = nalive | (uint32_t)avg << 16;
+                }
+            }
+            __syncwarp();
+            if (fighting) {
+                const uint32_t r = W.res[lane];
+                w1 = (w1 & 0xFFFF0000u) | (r & 0xFFFFu);  // alive == 0: destroyed, leaves the node list (:623-627)
+                w0 = (w0 & ~(127u << W0_AVG_SHIFT)) | ((r >> 16) & 127u) << W0_AVG_SHIFT;
+            }
+        }
+    }
+
+    // ---- movement, server.py:656-706 (destroyed groups are skipped, :663)
+    if (is_grp && (w1 & 0xFFFFu)) {
+        if (w0 & W0_READY) {
+            w0 = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
+        } else if (w0 & W0_MOVING) {
+            int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.ut_speed[gtype];  // :671
+            if (dist <= 0) {  // arrived: appended to the destination's list (:678-695)
+                const uint32_t dest = (w0 >> W0_DEST_SHIFT) & 0x3Fu;
+                w0 = (w0 & (127u << W0_AVG_SHIFT)) | dest;
+                w1 = (w1 & 0xFFFFu) | turn << 16;
+            } else {
+                w0 = (w0 & ~(0xFFu << W0_DIST_SHIFT)) | (uint32_t)dist << W0_DIST_SHIFT;
+            }
+        }
+    }
+
+    // ---- capture, server.py:708-767 (current_turn > 0 here; the turn-0 case is the reset kernel's)
+    node_accumulate(S, W, lane, is_grp, side, w0, w1, nn);
+    int s0 = 0, s1 = 0;
+    bool basecap = false;
+    if (lane < S.n_nodes) {
+        const int n = lane + 1;
+        int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
+        const uint32_t a0 = W.acc[n], a1 = W.acc[nn + n];
+        const bool c0 = (a0 >> 24) != 0, c1 = (a1 >> 24) != 0;
+        const int cp = S.node_cp[n];
+        if (c0 != c1) {  // exactly one controller (:729)
+            const int pid = c1 ? 1 : 0;
+            if (abs(cs) < cp || pid != cb) {  // :731-732
+                const int pts = (int)(((pid ? a1 : a0) >> 10) & 0x3FFFu), pxer = pid ? -1 : 1;
+                const bool old_sign = cs < 0;  // :747-750, zero counts as player 0's sign
+                cs += pts * pxer;
+                const bool neutralize = old_sign != (cs < 0);
+                if (abs(cs) >= cp) {  // :763-765
+                    cs = cp * pxer;
+                    cb = pid;
+                }
+                if (cb != -1 && neutralize) cb = -1;  // :766-767
+                nw = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
+            }
+        }
+        // ---- game_end scoring, server.py:298-310
+        const int ts = S.node_team_start[n];
+        if (ts != -1 && cb != -1 && cb != ts) {
+            basecap = true;
+            if (cb) s1 += S.capture_bonus; else s0 += S.capture_bonus;
+        }
+        if (cs != 0) {
+            const int pts = abs(cs) == cp ? 2 * cp : abs(cs);
+            if (cs > 0) s0 += pts; else s1 += pts;
+        }
+    }
+    const uint32_t galive_now = w1 & 0xFFFFu;
+    if (is_grp && galive_now) {  // server.py:313-317
+        const int v = __popc(galive_now) * (int)S.ut_cost[gtype];
+        if (side) s1 += v; else s0 += v;
+    }
+    s0 = __reduce_add_sync(FULL, s0);
+    s1 = __reduce_add_sync(FULL, s1);
+    const bool any_alive = __ballot_sync(FULL, is_grp && galive_now) != 0;
+    const bool any_basecap = __ballot_sync(FULL, basecap) != 0;
+    int status = EVG_STATUS_IN_PROGRESS;  // server.py:321-328, in that priority
+    if ((int)turn >= S.turn_limit) status = EVG_STATUS_TIME_EXPIRED;
+    else if (!any_alive) status = EVG_STATUS_ANNIHILATION;
+    else if (any_basecap) status = EVG_STATUS_BASE_CAPTURE;
+    const bool done = status != 0;
+
+    // ---- reward / done, env.py:37-60
+    if (lane < 2) {
+        const int mine = lane ? s1 : s0, other = lane ? s0 : s1;
+        float r;
+        if (done) r = mine == other ? 0.f : (mine > other ? 1.f : (lane ? -1.f : 0.f));
+        else r = (float)__ddiv_rn((double)mine, S.max_score);
+        A.reward[env * 2 + lane] = r;
+        if (A.scores) A.scores[env * 2 + lane] = mine;
+    }
+    if (lane == 0) {
+        A.done[env] = done ? 1 : 0;
+        if (A.status) A.status[env] = (uint8_t)status;
+    }
+
+    // ---- observations of the post-turn state
+    float* obs_out = A.obs + env * 2 * S.obs_len;
+    pack_obs(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, nn, obs_out);
+
+    // ---- termination with in-place auto-reset
+    if (done && S.auto_reset != EVG_AUTORESET_OFF) {
+        if (lane == 0) {
+            atomicAdd(&cta_stats[ST_EPISODES], 1ull);
+            atomicAdd(&cta_stats[s0 == s1 ? ST_TIES : (s0 > s1 ? ST_WIN0 : ST_WIN1)], 1ull);
+            atomicAdd(&cta_stats[ST_TURNS], (unsigned long long)turn);
+            atomicAdd(&cta_stats[ST_SCORE0], (unsigned long long)s0);
+            atomicAdd(&cta_stats[ST_SCORE1], (unsigned long long)s1);
+            atomicAdd(&cta_stats[ST_STATUS0 + status], 1ull);
+        }
+        if (is_grp) { w0 = S.init_w0[lane]; w1 = S.init_w1[lane]; }
+        if (lane < S.n_nodes) nw = S.init_node[lane + 1];
+        turn = 0;
+        episode += 1;
+        double* hp = A.health + env * S.health_slots;
+        for (int i = lane; i < S.health_slots; i += 32) hp[i] = 100.0;  // definitions.py:62
+        if (S.auto_reset == EVG_AUTORESET_NEXT) {
+            node_accumulate(S, W, lane, is_grp, side, w0, w1, nn);
+            pack_obs(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, nn, obs_out);
+        }
+    }
+
+    // ---- store the record
+    if (is_grp) { W.rec[2 * lane] = w0; W.rec[2 * lane + 1] = w1; }
+    if (lane < S.n_nodes) W.rec[kRecNode0 + lane] = nw;
+    if (lane == 0) { W.rec[kRecTurn] = turn; W.rec[kRecEpisode] = episode; }
+    __syncwarp();
+    for (int i = lane; i < S.rec_words8; i += 32) grec[i] = srec2[i];
+    __syncwarp();
+}
+
+__device__ __forceinline__ const Tables& stage_tables(const Tables& T, unsigned char* smem)
+{
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&T);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    return *reinterpret_cast<const Tables*>(smem);
+}
+
+__global__ void __launch_bounds__(kThreads) evg_step_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables& S = stage_tables(T, smem);
+    unsigned long long* cta_stats = reinterpret_cast<unsigned long long*>(smem + T.sm_tables_bytes);
+    if (threadIdx.x < ST_COUNT) cta_stats[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WarpSmem W = carve(smem + T.sm_tables_bytes + 128 + warp * T.sm_warp_stride, S);
+    for (int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + warp; env < A.n_envs; env += (int64_t)gridDim.x * kWarpsPerBlock)
+        step_match(S, W, A, env, lane, cta_stats);
+    __syncthreads();
+    if (threadIdx.x < ST_COUNT && cta_stats[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], cta_stats[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset: env.py:75-116 + server.py:133-209 (all groups at their base in gid order, health 100,
+// capture() at turn 0 -> bases at +-controlPoints); writes the first observation.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) evg_reset_kernel(const __grid_constant__ Tables T, uint32_t* records, double* health,
+                                                             const uint8_t* mask, float* obs, int64_t n_envs)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables& S = stage_tables(T, smem);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WarpSmem W = carve(smem + T.sm_tables_bytes + 128 + warp * T.sm_warp_stride, S);
+    const int nn = S.n_nodes + 1;
+    const bool is_grp = lane < kGroupLanes;
+    const int side = lane >= EVG_NUM_GROUPS ? 1 : 0, gid = lane - side * EVG_NUM_GROUPS;
+    for (int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + warp; env < n_envs; env += (int64_t)gridDim.x * kWarpsPerBlock) {
+        if (mask && !mask[env]) continue;
+        uint32_t* rec = records + env * S.rec_words8 * 2;
+        const uint32_t episode = mask ? rec[kRecEpisode] + 1u : 0u;
+        __syncwarp();
+        const uint32_t w0 = is_grp ? S.init_w0[lane] : 0u, w1 = is_grp ? S.init_w1[lane] : 0u;
+        const uint32_t nw = lane < S.n_nodes ? S.init_node[lane + 1] : 0u;
+        for (int i = lane; i < S.rec_words8 * 2; i += 32) {
+            uint32_t v = 0;
+            if (i < kRecGroupWords) v = (i & 1) ? S.init_w1[i >> 1] : S.init_w0[i >> 1];
+            else if (i == kRecEpisode) v = episode;
+            else if (i >= kRecNode0 && i < kRecNode0 + S.n_nodes) v = S.init_node[i - kRecNode0 + 1];
+            rec[i] = v;
+        }
+        double* hp = health + env * S.health_slots;
+        for (int i = lane; i < S.health_slots; i += 32) hp[i] = 100.0;
+        if (obs) {
+            node_accumulate(S, W, lane, is_grp, side, w0, w1, nn);
+            pack_obs(S, W, lane, is_grp, side, gid, w0, w1, nw, 0u, nn, obs + env * 2 * S.obs_len);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// export / import: resident layout <-> EvgEnvState (one thread per match; test and checkpoint path)
+// ---------------------------------------------------------------------------------------------
+__device__ double np_pairwise_sum(const double* a, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    const int m = n - (n % 8);
+    int i;
+    for (i = 8; i < m; i += 8)
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__global__ void evg_export_kernel(const __grid_constant__ Tables T, const uint32_t* records, const double* health, int64_t first,
+                                  int64_t count, EvgEnvState* out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t env = first + i;
+    const uint32_t* rec = records + env * T.rec_words8 * 2;
+    EvgEnvState* s = out + i;
+    s->turn = (int32_t)rec[kRecTurn];
+    s->episode = (int32_t)rec[kRecEpisode];
+    for (int n = 0; n <= EVG_MAX_NODES; ++n) {
+        s->control_state[n] = 0;
+        s->controlled_by[n] = -1;
+    }
+    for (int n = 1; n <= T.n_nodes; ++n) {
+        const uint32_t nw = rec[kRecNode0 + n - 1];
+        s->control_state[n] = (int16_t)(nw & 0xFFFFu);
+        s->controlled_by[n] = (int8_t)((nw >> 16) & 0xFFu);
+    }
+    for (int k = 0; k < 5; ++k) s->pad1[k] = 0;
+    for (int L = 0; L < kGroupLanes; ++L) {
+        const uint32_t w0 = rec[2 * L], w1 = rec[2 * L + 1];
+        EvgGroupState* g = &s->groups[L / EVG_NUM_GROUPS][L % EVG_NUM_GROUPS];
+        const uint32_t dest = (w0 >> W0_DEST_SHIFT) & 0x3Fu, alive = w1 & 0xFFFFu;
+        g->location = (int16_t)(w0 & W0_LOC_MASK);
+        g->travel_destination = dest ? (int16_t)dest : (int16_t)-1;
+        g->distance_remaining = (int16_t)((w0 >> W0_DIST_SHIFT) & 0xFFu);
+        g->ready = (w0 & W0_READY) ? 1 : 0;
+        g->moving = (w0 & W0_MOVING) ? 1 : 0;
+        g->destroyed = alive ? 0 : 1;
+        g->count = (uint8_t)__popc(alive);
+        g->arrival = (int32_t)((w1 >> 16) * 16u + (uint32_t)(L % EVG_NUM_GROUPS));
+        g->avg_health = (int32_t)((w0 >> W0_AVG_SHIFT) & 127u);
+        const double* hp = health + env * T.health_slots + T.g_slot[L];
+        for (int u = 0; u < EVG_MAX_GROUP_UNITS; ++u)
+            s->health[L / EVG_NUM_GROUPS][L % EVG_NUM_GROUPS][u] = u < T.g_size[L] ? hp[u] : 0.0;
+    }
+}
+
+__global__ void evg_import_kernel(const __grid_constant__ Tables T, uint32_t* records, double* health, int64_t first, int64_t count,
+                                  const EvgEnvState* in)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t env = first + i;
+    uint32_t* rec = records + env * T.rec_words8 * 2;
+    const EvgEnvState* s = in + i;
+    for (int k = kRecGroupWords; k < T.rec_words8 * 2; ++k) rec[k] = 0;
+    rec[kRecTurn] = (uint32_t)s->turn;
+    rec[kRecEpisode] = (uint32_t)s->episode;
+    for (int n = 1; n <= T.n_nodes; ++n)
+        rec[kRecNode0 + n - 1] = ((uint32_t)s->control_state[n] & 0xFFFFu) | ((uint32_t)s->controlled_by[n] & 0xFFu) << 16;
+    for (int L = 0; L < kGroupLanes; ++L) {
+        const EvgGroupState* g = &s->groups[L / EVG_NUM_GROUPS][L % EVG_NUM_GROUPS];
+        double* hp = health + env * T.health_slots + T.g_slot[L];
+        uint32_t alive = 0;
+        double tmp[EVG_MAX_GROUP_UNITS];
+        const int size = T.g_size[L];
+        for (int u = 0; u < size; ++u) {
+            const double h = s->health[L / EVG_NUM_GROUPS][L % EVG_NUM_GROUPS][u];
+            hp[u] = h;
+            tmp[u] = h;
+            if (h > 0.0) alive |= 1u << u;
+        }
+        // the cached observation field is derived state: recompute it (server.py:480-491)
+        const int avg = alive ? (int)__ddiv_rn(np_pairwise_sum(tmp, size), (double)__popc(alive)) : 0;
+        const uint32_t dest = g->travel_destination > 0 ? (uint32_t)g->travel_destination & 0x3Fu : 0u;
+        rec[2 * L] = ((uint32_t)g->location & W0_LOC_MASK) | dest << W0_DEST_SHIFT |
+                     ((uint32_t)g->distance_remaining & 0xFFu) << W0_DIST_SHIFT | (g->ready ? W0_READY : 0u) |
+                     (g->moving ? W0_MOVING : 0u) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
+        rec[2 * L + 1] = alive | (((uint32_t)g->arrival >> 4) & 0xFFFFu) << 16;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// random_actions agent (agents/State_Machine/random_actions.py:38-46): 7 distinct groups of 12 and
+// 7 distinct nodes of the map, paired in draw order, as a partial Fisher-Yates over the tape
+// (same function as evo_agent_random in oracle/evg_oracle.c).  One thread per (match, player).
+// ---------------------------------------------------------------------------------------------
+__global__ void evg_agent_random_kernel(const __grid_constant__ Tables T, const uint32_t* records, int8_t* actions, int player,
+                                        int64_t n_envs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nplayers = player < 0 ? 2 : 1;
+    if (i >= n_envs * nplayers) return;
+    const int64_t env = i / nplayers;
+    const int p = player < 0 ? (int)(i % nplayers) : player;
+    const uint32_t* rec = records + env * T.rec_words8 * 2;
+    const uint32_t turn = rec[kRecTurn] + 1u, episode = rec[kRecEpisode];
+    uint32_t w[16];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        philox4x32_10(T.env_base + (uint32_t)env, turn, (uint32_t)p | (uint32_t)b << 8, 1u | episode << 8, T.seed_lo, T.seed_hi,
+                      w + 4 * b);
+    // permutations kept as nibbles / bytes in registers: gp holds 12 group ids, nodes up to 32 ids
+    uint8_t gp[EVG_NUM_GROUPS], np_[EVG_MAX_NODES];
+#pragma unroll
+    for (int k = 0; k < EVG_NUM_GROUPS; ++k) gp[k] = (uint8_t)k;
+    for (int k = 0; k < T.n_nodes; ++k) np_[k] = (uint8_t)(k + 1);
+    int8_t* out = actions + (env * 2 + p) * (EVG_MAX_ACTIONS * 2);
+    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) {
+        const int j = k + (int)__umulhi(w[k], (uint32_t)(EVG_NUM_GROUPS - k));
+        const uint8_t t = gp[k]; gp[k] = gp[j]; gp[j] = t;
+        int node = 0;
+        if (k < T.n_nodes) {
+            const int q = k + (int)__umulhi(w[8 + k], (uint32_t)(T.n_nodes - k));
+            const uint8_t t2 = np_[k]; np_[k] = np_[q]; np_[q] = t2;
+            node = np_[k];
+        }
+        out[2 * k] = (int8_t)gp[k];
+        out[2 * k + 1] = (int8_t)node;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t set_step_smem(size_t smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(evg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(evg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t step_occupancy(size_t smem, int* blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_kernel, kThreads, smem);
+}
+
+cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t smem, cudaStream_t stream)
+{
+    evg_step_kernel<<<grid, kThreads, smem, stream>>>(t, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, float* obs, int64_t n_envs,
+                         int grid, size_t smem, cudaStream_t stream)
+{
+    evg_reset_kernel<<<grid, kThreads, smem, stream>>>(t, records, health, mask, obs, n_envs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export(const Tables& t, const uint32_t* records, const double* health, int64_t first, int64_t count,
+                          EvgEnvState* out, cudaStream_t stream)
+{
+    if (count <= 0) return cudaSuccess;
+    evg_export_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(t, records, health, first, count, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_import(const Tables& t, uint32_t* records, double* health, int64_t first, int64_t count,
+                          const EvgEnvState* in, cudaStream_t stream)
+{
+    if (count <= 0) return cudaSuccess;
+    evg_import_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(t, records, health, first, count, in);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t* actions, int player, int64_t n_envs,
+                                cudaStream_t stream)
+{
+    const int64_t n = n_envs * (player < 0 ? 2 : 1);
+    if (n <= 0) return cudaSuccess;
+    evg_agent_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(t, records, actions, player, n_envs);
+    return cudaGetLastError();
+}
+
+}  // namespace evg

@@ -1,0 +1,320 @@
+"""Host-side mirror of the reference's gym wrapper on top of libevgsim (CUDA, sm_100a).
+
+``EvergladesEnv``         — same attributes, ``reset(**kwargs)`` / ``step(actions)`` signatures, dict-in
+                            / dict-out types and error behaviour as
+                            gym_everglades/envs/everglades_env.py:13-116, for ONE match (N = 1).
+``BatchedEvergladesEnv``  — N matches in lockstep on one GPU; tensors in, tensors out.
+
+PyTorch is plumbing only (device memory, streams); every game rule runs in the kernels of
+csrc/evg_kernels.cu through the C ABI of include/evgsim.h.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .config import load_config, UNIT_CLASSES, MAX_SCORE  # noqa: F401  (MAX_SCORE re-exported, env.py:11)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class BatchedEvergladesEnv:
+    """N Everglades matches stepped in lockstep by one CUDA launch per turn.
+
+    Shapes (L = obs_len = 1 + 4*num_nodes + 60; 105 on DemoMap):
+        actions int8    [N, 2, 7, 2]   (group id, node id in the acting player's own numbering)
+        obs     float32 [N, 2, L]      layout of env.py:158-171 (board_state[0:45] ++ player_state[1:61])
+        reward  float32 [N, 2]         env.py:37-60
+        done    uint8   [N]            status != 0 (server.py:321-328)
+    Output tensors are allocated once and overwritten in place by every call.
+    """
+
+    def __init__(self, num_envs, device=0, seed=0, config_dir=None, map_file="DemoMap.json",
+                 unit_file="UnitDefinitions.json", setup_file="GameSetup.json", auto_reset=_capi.AUTORESET_OFF,
+                 env_id_offset=0, config=None):
+        torch = _torch()
+        self._lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedEvergladesEnv needs a CUDA device: the game step has no CPU implementation")
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.cfg = config if config is not None else load_config(config_dir, map_file, unit_file, setup_file, auto_reset)
+        if config is not None:
+            self.cfg.auto_reset = int(auto_reset) if auto_reset is not None else self.cfg.auto_reset
+        self.num_envs = int(num_envs)
+        self.seed = int(seed)
+        self.env_id_offset = int(env_id_offset)
+        self._h = C.c_void_p()
+        _capi.check(self._lib.evg_create(C.byref(self.cfg), self.num_envs, self.seed, self.env_id_offset, dev_index,
+                                         C.byref(self._h)))
+        lay = _capi.EvgLayout()
+        _capi.check(self._lib.evg_layout(self._h, C.byref(lay)))
+        self.layout = lay
+        self.obs_len = int(lay.obs_len)
+        # reference attributes (env.py:17-22)
+        self.num_turns = int(self.cfg.turn_limit)
+        self.num_groups = _capi.NUM_GROUPS
+        self.num_nodes = int(self.cfg.n_nodes)
+        self.num_units = int(sum(self.cfg.group_size[0]))
+        self.num_actions_per_turn = _capi.MAX_ACTIONS
+        self.unit_classes = list(UNIT_CLASSES)
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            # resident state: owned here, only ever touched by the kernels
+            self._records = torch.empty(lay.records_bytes, dtype=torch.uint8, device=self.device)
+            self._health = torch.empty(lay.health_bytes // 8, dtype=torch.float64, device=self.device)
+            self._stats = torch.zeros(lay.stats_bytes // 8, dtype=torch.int64, device=self.device)
+            self.obs = torch.empty((N, 2, self.obs_len), dtype=torch.float32, device=self.device)
+            self.reward = torch.empty((N, 2), dtype=torch.float32, device=self.device)
+            self.done = torch.empty((N,), dtype=torch.uint8, device=self.device)
+            self.status = torch.empty((N,), dtype=torch.uint8, device=self.device)
+            self.scores = torch.empty((N, 2), dtype=torch.int32, device=self.device)
+            self._actions = torch.zeros((N, 2, _capi.MAX_ACTIONS, 2), dtype=torch.int8, device=self.device)
+        ptrs = (C.c_void_p * _capi.BIND_COUNT)(self._records.data_ptr(), self._health.data_ptr(), self._stats.data_ptr())
+        _capi.check(self._lib.evg_bind(self._h, ptrs, _capi.BIND_COUNT))
+        self._host = None
+        self._is_reset = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.evg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.evg_launch_count(self._h))
+
+    def _as_actions(self, actions):
+        torch = _torch()
+        shape = (self.num_envs, 2, _capi.MAX_ACTIONS, 2)
+        if isinstance(actions, torch.Tensor) and actions.dtype == torch.int8 and actions.device == self.device \
+                and tuple(actions.shape) == shape and actions.is_contiguous():
+            return actions
+        a = torch.as_tensor(actions)
+        if tuple(a.shape) != shape:
+            raise ValueError("actions must have shape %s, got %s" % (shape, tuple(a.shape)))
+        # astype(int) truncation toward zero (server.py:232), then saturate into int8 (out-of-range rows are no-ops)
+        a = a.to(self.device)
+        if a.is_floating_point():
+            a = a.trunc()
+        self._actions.copy_(a.clamp(-128, 127).to(torch.int8))
+        return self._actions
+
+    # ------------------------------------------------------------------ reference-shaped API
+    def reset(self, mask=None):
+        """All matches (mask None) or the masked ones go back to the game_init state; returns obs."""
+        torch = _torch()
+        mptr = None
+        if mask is not None:
+            mask = torch.as_tensor(mask).to(self.device).ne(0).to(torch.uint8).contiguous()
+            if tuple(mask.shape) != (self.num_envs,):
+                raise ValueError("mask must have shape (%d,)" % self.num_envs)
+            mptr = C.c_void_p(mask.data_ptr())
+        _capi.check(self._lib.evg_reset(self._h, mptr, C.c_void_p(self.obs.data_ptr()), self._stream()))
+        self._is_reset = True
+        return self.obs
+
+    def step(self, actions):
+        """One game turn for every match. Returns (obs, reward, done, info) — tensors, overwritten in place."""
+        if not self._is_reset:
+            raise RuntimeError("call reset() before step()")
+        a = self._as_actions(actions)
+        _capi.check(self._lib.evg_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                                       C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                       C.c_void_p(self.status.data_ptr()), C.c_void_p(self.scores.data_ptr()),
+                                       self._stream()))
+        return self.obs, self.reward, self.done, {"status": self.status, "scores": self.scores}
+
+    # ------------------------------------------------------------------ host-buffer path (end-to-end)
+    def host_buffers(self):
+        """Pinned host arrays for step_host: actions int8[N,2,7,2] in; obs, reward, done out."""
+        if self._host is None:
+            torch = _torch()
+            N = self.num_envs
+            self._host = {
+                "actions": torch.zeros((N, 2, _capi.MAX_ACTIONS, 2), dtype=torch.int8).pin_memory(),
+                "obs": torch.empty((N, 2, self.obs_len), dtype=torch.float32).pin_memory(),
+                "reward": torch.empty((N, 2), dtype=torch.float32).pin_memory(),
+                "done": torch.empty((N,), dtype=torch.uint8).pin_memory(),
+            }
+        return self._host
+
+    def step_host(self, actions=None, sync=True):
+        """Same turn through HOST memory: H2D actions, step, D2H obs/reward/done (evg_step_host).
+
+        `actions`: None (use host_buffers()['actions'] as filled by the caller) or an array copied into
+        it.  Returns the pinned host tensors (valid after the stream is synchronised; sync=True does it).
+        """
+        if not self._is_reset:
+            raise RuntimeError("call reset() before step()")
+        torch = _torch()
+        hb = self.host_buffers()
+        if actions is not None:
+            hb["actions"].copy_(torch.as_tensor(actions).to(torch.int8).reshape(hb["actions"].shape))
+        _capi.check(self._lib.evg_step_host(
+            self._h, C.c_void_p(hb["actions"].data_ptr()), C.c_void_p(hb["obs"].data_ptr()),
+            C.c_void_p(hb["reward"].data_ptr()), C.c_void_p(hb["done"].data_ptr()),
+            C.c_void_p(self._actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+            C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), self._stream()))
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return hb["obs"], hb["reward"], hb["done"], {}
+
+    def h2d_bytes_per_step(self) -> int:
+        return self.num_envs * int(self.layout.action_bytes)
+
+    def d2h_bytes_per_step(self) -> int:
+        return self.num_envs * (2 * self.obs_len * 4 + 2 * 4 + 1)
+
+    # ------------------------------------------------------------------ scripted agents on the device
+    def random_actions(self, player=-1, out=None):
+        """random_actions agent (agents/State_Machine/random_actions.py:38-46) for `player` (-1 = both)."""
+        out = self._actions if out is None else out
+        _capi.check(self._lib.evg_agent_random(self._h, C.c_void_p(out.data_ptr()), int(player), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ snapshots
+    def get_state(self, first=0, count=None):
+        """numpy structured array (dtype _capi.env_state_dtype()) of matches [first, first+count)."""
+        torch = _torch()
+        count = self.num_envs - first if count is None else count
+        dt = _capi.env_state_dtype()
+        buf = torch.empty(count * dt.itemsize, dtype=torch.uint8, device=self.device)
+        _capi.check(self._lib.evg_export_state(self._h, first, count, C.c_void_p(buf.data_ptr()), self._stream()))
+        return buf.cpu().numpy().view(dt).copy()
+
+    def set_state(self, states, first=0):
+        torch = _torch()
+        dt = _capi.env_state_dtype()
+        states = np.ascontiguousarray(states)
+        assert states.dtype == dt
+        buf = torch.from_numpy(states.view(np.uint8).reshape(-1).copy()).to(self.device)
+        _capi.check(self._lib.evg_import_state(self._h, first, len(states), C.c_void_p(buf.data_ptr()), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        self._is_reset = True
+
+    def episode_stats(self) -> dict:
+        st = _capi.EvgEpisodeStats()
+        _capi.check(self._lib.evg_episode_stats(self._h, C.byref(st), self._stream()))
+        return {"episodes": st.episodes, "wins": [st.wins[0], st.wins[1]], "ties": st.ties,
+                "total_turns": st.total_turns, "total_score": [st.total_score[0], st.total_score[1]],
+                "status_count": [st.status_count[i] for i in range(4)], "env_turns": st.env_turns}
+
+
+class EvergladesEnv:
+    """Drop-in for ``gym_everglades.envs.EvergladesEnv`` (env.py:13-116), one match on the GPU.
+
+    Same attributes (env.py:17-28), ``reset(**kwargs) -> {pid: float64[105]}`` and
+    ``step({pid: array[k,2]}) -> (obs, reward, done, {})`` with the reference's types and error
+    behaviour: AssertionError for != 2 players (env.py:87) or != 2 action columns (server.py:226),
+    IndexError for group ids outside [-12, 11] and player-1 node ids outside [-12, 11]
+    (server.py:92,235; negative ids wrap like Python lists).  ``render``/``close`` are no-ops (the
+    pyglet viewer is out of scope).  Combat randomness comes from the Philox tape keyed on `seed`.
+    """
+
+    def __init__(self, device=0, seed=0):
+        self.num_turns = 150
+        self.num_units = 100
+        self.num_groups = 12
+        self.num_nodes = 11
+        self.num_actions_per_turn = 7
+        self.unit_classes = list(UNIT_CLASSES)
+        self.action_space = tuple((self.num_groups, self.num_nodes + 1) for _ in range(self.num_actions_per_turn))
+        self.observation_space = self._build_observation_space()
+        self.viewer = None
+        self._device, self._seed = device, seed
+        self._env = None
+
+    def _build_observation_space(self):
+        """(low, high) bounds as env.py:124-143 declares them (controlState of bases exceeds them: SURVEY A.5)."""
+        group_low = np.array([1, 0, 0, 0, 0])
+        group_high = np.array([self.num_nodes, len(self.unit_classes), 100, 1, self.num_units])
+        cp_low = np.array([0, 0, -100, -1])
+        cp_high = np.array([1, 1, 100, self.num_units])
+        low = np.concatenate([[1], np.tile(cp_low, self.num_nodes), np.tile(group_low, self.num_groups)])
+        high = np.concatenate([[self.num_turns + 1], np.tile(cp_high, self.num_nodes), np.tile(group_high, self.num_groups)])
+        return low, high
+
+    def reset(self, **kwargs):
+        self.players = kwargs.get("players")
+        config_dir = kwargs.get("config_dir")
+        map_file = kwargs.get("map_file") or "DemoMap.json"
+        unit_file = kwargs.get("unit_file") or "UnitDefinitions.json"
+        self.debug = kwargs.get("debug", False)  # accepted and, as in the reference, without effect on obs
+        assert len(self.players) == 2, "Must have exactly two players"  # env.py:87
+        self.pks = self.players.keys()
+        self.sorted_pks = sorted(self.pks)
+        for p in self.pks:
+            assert p in (0, 1), "Given player number not included in map configuration file starting locations"
+        cfg = load_config(config_dir, map_file, unit_file, kwargs.get("setup_file", "GameSetup.json"))
+        if self._env is not None:
+            self._env.close()
+        self._env = BatchedEvergladesEnv(1, device=self._device, seed=self._seed, config=cfg,
+                                         auto_reset=_capi.AUTORESET_OFF,
+                                         env_id_offset=kwargs.get("env_id", 0))
+        self.num_nodes = self._env.num_nodes
+        self.num_turns = self._env.num_turns
+        self.num_units = self._env.num_units
+        obs = self._env.reset()
+        return self._obs_dict(obs)
+
+    def _obs_dict(self, obs):
+        o = obs[0].to("cpu").numpy().astype(np.float64)
+        return {p: o[p].copy() for p in self.players}
+
+    def step(self, actions):
+        rows = np.zeros((1, 2, _capi.MAX_ACTIONS, 2), dtype=np.int8)
+        for player in (0, 1):  # server.py:218-221
+            if player not in actions:
+                print("Player {} not found in input action dictionary".format(player))
+                continue
+            action = np.asarray(actions[player])
+            r, c = action.shape[:2]
+            assert c == 2, "Did not receive 2 columns for player {}s action".format(player)  # server.py:226
+            action = action[:7, :].astype(int)  # server.py:227,232
+            for i, (gid, nid) in enumerate(action):
+                if not -self.num_groups <= gid < self.num_groups:
+                    raise IndexError("list index out of range")  # players[player].groups[gid], server.py:235
+                gid = gid % self.num_groups
+                if player == 1:
+                    if not -(self.num_nodes + 1) <= nid <= self.num_nodes:
+                        raise IndexError("list index out of range")  # p1_node_map[int(nid)], server.py:92
+                    nid = nid % (self.num_nodes + 1)
+                rows[0, player, i] = (gid, nid if 0 <= nid <= 127 else 0)
+        obs, _, done, info = self._env.step(rows)
+        scores = info["scores"][0].to("cpu").numpy()
+        status = int(info["status"][0])
+        reward = {i: 0 for i in self.players}
+        done = 0
+        if status != 0:  # env.py:39-46
+            done = 1
+            if scores[0] != scores[1]:
+                reward[0] = 1 if scores[0] > scores[1] else 0
+                reward[1] = 1 if scores[1] > scores[0] else -1
+        else:  # env.py:58-60
+            reward[0] = int(scores[0]) / MAX_SCORE
+            reward[1] = int(scores[1]) / MAX_SCORE
+        return self._obs_dict(obs), reward, done, {}
+
+    def render(self, mode="human"):
+        return None
+
+    def close(self):
+        if self._env is not None:
+            self._env.close()
+            self._env = None

@@ -503,5 +503,30 @@ int64_t evo_run_random(const EvgConfig* c, uint64_t seed, int64_t first, int64_t
     return n;
 }
 
+/* ------------------------------------------------------------------ lock-step batch (parity tests)
+ * Steps matches first..first+n-1 (global ids) one turn each; int8 actions [n][2][7][2]; on done and
+ * auto_reset != 0 the match is reset in place (episode + 1) exactly as the CUDA path does:
+ * mode 1 keeps the terminal observation, mode 2 replaces it by the first observation of the new match. */
+void evo_step_batch(const EvgConfig* c, EvgEnvState* states, int64_t n, uint64_t seed, int64_t first, const int8_t* actions,
+                    double* obs, double* reward, uint8_t* done, int32_t* scores_out, uint8_t* status_out)
+{
+    int len = evo_obs_len(c);
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t act[2 * EVG_MAX_ACTIONS * 2];
+        for (int k = 0; k < 2 * EVG_MAX_ACTIONS * 2; ++k) act[k] = actions[i * 2 * EVG_MAX_ACTIONS * 2 + k];
+        int64_t sc[2];
+        int status;
+        int d = evo_step(c, &states[i], seed, (uint64_t)(first + i), act, EVG_MAX_ACTIONS, obs + i * 2 * len, reward + 2 * i, sc,
+                         &status);
+        done[i] = (uint8_t)d;
+        if (scores_out) { scores_out[2 * i] = (int32_t)sc[0]; scores_out[2 * i + 1] = (int32_t)sc[1]; }
+        if (status_out) status_out[i] = (uint8_t)status;
+        if (d && c->auto_reset != EVG_AUTORESET_OFF) {
+            evo_reset(c, &states[i], states[i].episode + 1);
+            if (c->auto_reset == EVG_AUTORESET_NEXT) evo_observe(c, &states[i], obs + i * 2 * len);
+        }
+    }
+}
+
 int evo_sizeof_config(void) { return (int)sizeof(EvgConfig); }
 int evo_sizeof_state(void) { return (int)sizeof(EvgEnvState); }

@@ -48,6 +48,8 @@ def lib():
         L.evo_run_random.argtypes = [C.POINTER(_capi.EvgConfig), C.c_uint64, C.c_int64, C.c_int64, C.c_int,
                                      C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.evo_run_random.restype = C.c_int64
+        L.evo_step_batch.argtypes = [C.POINTER(_capi.EvgConfig), P, C.c_int64, C.c_uint64, C.c_int64, P, P, P, P, P, P]
+        L.evo_step_batch.restype = None
         L.evo_philox.argtypes = [P, P, P]
         L.evo_philox.restype = None
         assert L.evo_sizeof_config() == C.sizeof(_capi.EvgConfig)
@@ -90,6 +92,41 @@ class OracleEnv:
                               a.shape[1], obs.ctypes.data_as(C.c_void_p), reward.ctypes.data_as(C.c_void_p),
                               scores.ctypes.data_as(C.c_void_p), C.byref(status))
         return obs, reward, int(done), scores, status.value
+
+
+class OracleBatch:
+    """n matches with global ids first..first+n-1 stepped in lock-step on the CPU oracle."""
+
+    def __init__(self, cfg, n, seed=0, first=0):
+        self.cfg, self.n, self.seed, self.first = cfg, int(n), int(seed), int(first)
+        self.obs_len = lib().evo_obs_len(C.byref(cfg))
+        self.states = np.zeros(self.n, dtype=_capi.env_state_dtype())
+        self.obs = np.zeros((self.n, 2, self.obs_len), dtype=np.float64)
+        self.reward = np.zeros((self.n, 2), dtype=np.float64)
+        self.done = np.zeros(self.n, dtype=np.uint8)
+        self.scores = np.zeros((self.n, 2), dtype=np.int32)
+        self.status = np.zeros(self.n, dtype=np.uint8)
+
+    def _p(self, a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def reset(self, mask=None):
+        st = self.states
+        for i in range(self.n):
+            if mask is None or mask[i]:
+                ep = 0 if mask is None else int(st[i]["episode"]) + 1
+                lib().evo_reset(C.byref(self.cfg), C.c_void_p(st.ctypes.data + i * st.itemsize), ep)
+                lib().evo_observe(C.byref(self.cfg), C.c_void_p(st.ctypes.data + i * st.itemsize),
+                                  C.c_void_p(self.obs.ctypes.data + i * self.obs[0].nbytes))
+        return self.obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.int8))
+        assert a.shape == (self.n, 2, 7, 2)
+        lib().evo_step_batch(C.byref(self.cfg), self._p(self.states), self.n, self.seed, self.first, self._p(a),
+                             self._p(self.obs), self._p(self.reward), self._p(self.done), self._p(self.scores),
+                             self._p(self.status))
+        return self.obs, self.reward, self.done
 
 
 def agent_random(cfg, seed, env_id, episode, turn, player):

@@ -1,0 +1,252 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden trajectories and with the
+CPU oracle on the same seeded inputs.  Bar: BIT-EXACT for observations, rewards (float32 of the
+reference's float64), done flags, every integer state field, node-list order and fp64 unit health.
+"""
+import numpy as np
+import pytest
+
+from conftest import state_fields, flat_health
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def evg():
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+    return evgsim
+
+
+@pytest.fixture(scope="module")
+def eo():
+    from oracle import evg_oracle
+    return evg_oracle
+
+
+def rank_of(states):
+    from oracle import evg_oracle
+    return np.stack([evg_oracle.list_rank(s) for s in states])
+
+
+def assert_states_equal(gpu, ora, where=""):
+    for name in ("turn", "episode", "control_state", "controlled_by", "health"):
+        assert np.array_equal(gpu[name], ora[name]), (where, name)
+    for name in ("location", "travel_destination", "distance_remaining", "ready", "moving", "destroyed", "count",
+                 "arrival", "avg_health"):
+        assert np.array_equal(gpu["groups"][name], ora["groups"][name]), (where, name)
+
+
+# --------------------------------------------------------------------------------------------- golden
+def test_golden_trajectories_bit_exact(evg, golden, cfg):
+    """All 37 reference games replayed as ONE lock-step batch (match id i = fixture game i)."""
+    n = len(golden)
+    env = evg.BatchedEvergladesEnv(n, seed=golden.seed)
+    obs = env.reset().cpu().numpy()
+    for i, g in enumerate(golden.games):
+        assert np.array_equal(obs[i], g["obs"][0].astype(np.float32)), i
+    T = max(len(g["done"]) for g in golden.games)
+    checked = 0
+    for t in range(T):
+        acts = np.zeros((n, 2, 7, 2), dtype=np.int8)
+        for i, g in enumerate(golden.games):
+            if t < len(g["done"]):
+                acts[i] = g["actions"][t][:, :7, :]
+        obs, rew, done, info = env.step(acts)
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        st = env.get_state()
+        for i, g in enumerate(golden.games):
+            if t >= len(g["done"]):
+                continue
+            where = "game %d (%s) turn %d" % (i, golden.names[i], t + 1)
+            assert np.array_equal(obs[i], g["obs"][t + 1].astype(np.float32)), where
+            assert np.array_equal(rew[i], g["reward"][t].astype(np.float32)), where
+            assert done[i] == g["done"][t], where
+            assert np.array_equal(state_fields(st[i]), g["grp"][t + 1]), where
+            assert np.array_equal(st[i]["control_state"][1:12], g["node"][t + 1][:, 0]), where
+            assert np.array_equal(st[i]["controlled_by"][1:12], g["node"][t + 1][:, 1]), where
+            assert np.array_equal(flat_health(st[i], cfg), g["health"][t + 1]), where
+            assert np.array_equal(rank_of(st[i:i + 1])[0], g["rank"][t + 1]), where
+            checked += 1
+    assert checked == sum(len(g["done"]) for g in golden.games)
+
+
+# --------------------------------------------------------------------------------------------- oracle, at scale
+def adjacent_actions(rng, states, cfg, p_move=0.9):
+    """7 random groups per player, each sent to a random neighbour of where it stands (own numbering)."""
+    n = len(states)
+    adj = [[b for b in range(1, cfg.n_nodes + 1) if cfg.edge_distance[a][b]] or [0] for a in range(cfg.n_nodes + 1)]
+    maxd = max(len(a) for a in adj)
+    table = np.zeros((cfg.n_nodes + 1, maxd), dtype=np.int64)
+    deg = np.zeros(cfg.n_nodes + 1, dtype=np.int64)
+    for a, nb in enumerate(adj):
+        table[a, :len(nb)] = nb
+        deg[a] = len(nb)
+    p1map = np.array(list(cfg.p1_node_map)[:cfg.n_nodes + 1])
+    acts = np.zeros((n, 2, 7, 2), dtype=np.int8)
+    loc = states["groups"]["location"].astype(np.int64)  # [n,2,12]
+    for p in range(2):
+        gids = np.argsort(rng.random((n, 12)), axis=1)[:, :7]
+        l = np.take_along_axis(loc[:, p], gids, axis=1)
+        pick = (rng.random((n, 7)) * deg[l]).astype(np.int64)
+        real = table[l, pick]
+        node = p1map[real] if p else real
+        node = np.where(rng.random((n, 7)) < p_move, node, 0)
+        acts[:, p, :, 0] = gids
+        acts[:, p, :, 1] = node
+    return acts
+
+
+def uniform_actions(rng, n, n_nodes=11):
+    acts = np.zeros((n, 2, 7, 2), dtype=np.int8)
+    for p in range(2):
+        acts[:, p, :, 0] = np.argsort(rng.random((n, 12)), axis=1)[:, :7]
+        acts[:, p, :, 1] = np.argsort(rng.random((n, n_nodes)), axis=1)[:, :7] + 1
+    return acts
+
+
+def run_against_oracle(evg, eo, cfg, n, turns, seed, first, make_actions, auto_reset=0, state_every=10):
+    cfg.auto_reset = auto_reset
+    env = evg.BatchedEvergladesEnv(n, seed=seed, config=cfg, auto_reset=auto_reset, env_id_offset=first)
+    ora = eo.OracleBatch(cfg, n, seed=seed, first=first)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
+    ndone = 0
+    for t in range(turns):
+        acts = make_actions(ora.states)
+        obs, rew, done, info = env.step(acts)
+        oobs, orew, odone = ora.step(acts)
+        where = "turn %d" % (t + 1)
+        assert np.array_equal(done.cpu().numpy(), odone), where
+        assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), where
+        assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), where
+        assert np.array_equal(info["scores"].cpu().numpy(), ora.scores), where
+        assert np.array_equal(info["status"].cpu().numpy(), ora.status), where
+        ndone += int(odone.sum())
+        if (t + 1) % state_every == 0 or t == turns - 1:
+            assert_states_equal(env.get_state(), ora.states, where)
+    return env, ora, ndone
+
+
+def test_oracle_parity_4096_adjacent_random(evg, eo, cfg):
+    """BASELINE config 2 size: 4096 lock-step matches, a full 150-turn episode, heavy traffic/combat."""
+    rng = np.random.default_rng(1)
+    run_against_oracle(evg, eo, cfg, 4096, 150, seed=11, first=0, make_actions=lambda s: adjacent_actions(rng, s, cfg))
+
+
+def test_oracle_parity_uniform_random_with_offset(evg, eo, cfg):
+    """random_actions-style rows (mostly invalid moves), match ids starting at a large offset."""
+    rng = np.random.default_rng(2)
+    run_against_oracle(evg, eo, cfg, 1024, 150, seed=0xDEADBEEFCAFE, first=3_000_000_000,
+                       make_actions=lambda s: uniform_actions(rng, len(s)))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_auto_reset_modes_match_oracle(evg, eo, cfg, mode):
+    """In-place auto-reset (terminal obs / next obs) over several episodes, incl. episode statistics."""
+    rng = np.random.default_rng(3 + mode)
+    cfg.turn_limit = 40
+    try:
+        env, ora, ndone = run_against_oracle(evg, eo, cfg, 512, 130, seed=5, first=17,
+                                             make_actions=lambda s: adjacent_actions(rng, s, cfg), auto_reset=mode)
+    finally:
+        cfg.turn_limit = 150
+        cfg.auto_reset = 0
+    st = env.episode_stats()
+    assert st["episodes"] == ndone >= 3 * 512
+    assert st["wins"][0] + st["wins"][1] + st["ties"] == ndone
+    assert sum(st["status_count"]) == ndone and st["status_count"][0] == 0
+    assert st["env_turns"] == 512 * 130
+    assert (ora.states["episode"] >= 3).all()
+
+
+def test_out_of_range_rows_are_noops(evg, eo, cfg):
+    """Rows the reference answers with IndexError are ignored (documented divergence) — same as the oracle."""
+    rng = np.random.default_rng(9)
+
+    def make(states):
+        a = adjacent_actions(rng, states, cfg)
+        n = len(states)
+        junk = rng.random((n, 2, 7)) < 0.3
+        a[..., 0] = np.where(junk, rng.integers(-128, 128, (n, 2, 7)), a[..., 0])
+        junk = rng.random((n, 2, 7)) < 0.3
+        a[..., 1] = np.where(junk, rng.integers(-128, 128, (n, 2, 7)), a[..., 1])
+        dup = rng.random((n, 2)) < 0.5
+        a[:, :, 1, 0] = np.where(dup, a[:, :, 0, 0], a[:, :, 1, 0])
+        return a.astype(np.int8)
+
+    run_against_oracle(evg, eo, cfg, 512, 100, seed=21, first=0, make_actions=make)
+
+
+def test_import_export_roundtrip_and_resume(evg, eo, cfg):
+    """evg_export_state / evg_import_state: a mid-game oracle snapshot resumes identically on the GPU."""
+    rng = np.random.default_rng(4)
+    n = 256
+    ora = eo.OracleBatch(cfg, n, seed=8, first=100)
+    ora.reset()
+    for t in range(60):
+        ora.step(adjacent_actions(rng, ora.states, cfg))
+    env = evg.BatchedEvergladesEnv(n, seed=8, config=cfg, env_id_offset=100)
+    env.reset()
+    env.set_state(ora.states)
+    assert_states_equal(env.get_state(), ora.states, "after import")
+    for t in range(60):
+        acts = adjacent_actions(rng, ora.states, cfg)
+        obs, rew, done, _ = env.step(acts)
+        oobs, orew, odone = ora.step(acts)
+        assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+        assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
+    assert_states_equal(env.get_state(), ora.states, "after resume")
+
+
+def test_masked_reset(evg, eo, cfg):
+    rng = np.random.default_rng(6)
+    n = 128
+    env = evg.BatchedEvergladesEnv(n, seed=2, config=cfg)
+    ora = eo.OracleBatch(cfg, n, seed=2)
+    env.reset()
+    ora.reset()
+    for t in range(30):
+        acts = adjacent_actions(rng, ora.states, cfg)
+        env.step(acts)
+        ora.step(acts)
+    mask = rng.random(n) < 0.5
+    obs = env.reset(mask).cpu().numpy()
+    oobs = ora.reset(mask)
+    assert np.array_equal(obs[mask], oobs[mask].astype(np.float32))
+    assert_states_equal(env.get_state(), ora.states, "after masked reset")
+    for t in range(30):
+        acts = adjacent_actions(rng, ora.states, cfg)
+        obs, _, _, _ = env.step(acts)
+        oobs, _, _ = ora.step(acts)
+        assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+
+
+def test_random_agent_kernel_matches_oracle(evg, eo, cfg):
+    n = 300
+    env = evg.BatchedEvergladesEnv(n, seed=77, config=cfg, env_id_offset=5)
+    env.reset()
+    for turn in (1, 2):
+        a = env.random_actions().cpu().numpy()
+        for i in range(n):
+            for p in range(2):
+                want = eo.agent_random(cfg, 77, 5 + i, 0, turn, p)
+                assert np.array_equal(a[i, p], want.astype(np.int8)), (i, p)
+        assert all(len(set(a[i, p, :, 0])) == 7 and len(set(a[i, p, :, 1])) == 7 for i in range(n) for p in range(2))
+        env.step(a)
+
+
+def test_step_host_equals_step(evg, eo, cfg):
+    rng = np.random.default_rng(12)
+    n = 200
+    env = evg.BatchedEvergladesEnv(n, seed=3, config=cfg)
+    ora = eo.OracleBatch(cfg, n, seed=3)
+    env.reset()
+    ora.reset()
+    for t in range(40):
+        acts = adjacent_actions(rng, ora.states, cfg)
+        obs, rew, done, _ = env.step_host(acts)
+        oobs, orew, odone = ora.step(acts)
+        assert np.array_equal(obs.numpy(), oobs.astype(np.float32))
+        assert np.array_equal(rew.numpy(), orew.astype(np.float32))
+        assert np.array_equal(done.numpy(), odone)
+    assert env.h2d_bytes_per_step() == n * 28 and env.d2h_bytes_per_step() == n * (840 + 8 + 1)
