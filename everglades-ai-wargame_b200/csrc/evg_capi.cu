@@ -66,7 +66,8 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.turn_limit = c.turn_limit;
     t.capture_bonus = c.capture_bonus;
     t.auto_reset = c.auto_reset;
-    t.max_score = (double)c.max_score;
+    if (c.max_score >= (1 << 24)) return fail(EVG_E_CONFIG, "max_score %d must be below 2^24", c.max_score);
+    t.max_score_f = (float)c.max_score;
     t.seed_lo = (uint32_t)seed;
     t.seed_hi = (uint32_t)(seed >> 32);
     t.env_base = (uint32_t)env_id_offset;
@@ -110,6 +111,10 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
             if (type >= c.n_unit_types) return fail(EVG_E_CONFIG, "group %d of player %d has unknown unit type %d", g, p, type);
             t.g_type[L] = (uint8_t)type;
             t.g_size[L] = (uint8_t)size;
+            t.g_damage[L] = t.ut_damage[type];
+            t.g_speed[L] = t.ut_speed[type];
+            t.g_control[L] = t.ut_control[type];
+            t.g_cost[L] = t.ut_cost[type];
             t.g_slot[L] = (uint16_t)slots;  // per-player offset for now
             slots += round_up(size, 4);     // every group starts on a 32-byte sector
             units += size;
@@ -145,7 +150,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.sm_hist = t.sm_acc + round_up(2 * nn * 4, 16);
     t.sm_obs = t.sm_hist + round_up(2 * t.hist_words * 4, 16);
     t.sm_misc = t.sm_obs + round_up(2 * t.obs_len * 4, 16);
-    t.sm_warp_stride = t.sm_misc + round_up(256 + 2 * nn, 16);
+    t.sm_warp_stride = t.sm_misc + 480;
     t.sm_tables_bytes = round_up((int)sizeof(evg::Tables), 16);
     *out = t;
     return EVG_OK;
@@ -246,7 +251,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     s->smem = (size_t)t.sm_tables_bytes + 128 + (size_t)evg::kWarpsPerBlock * t.sm_warp_stride;
     if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
     int per_sm = 0;
-    if ((e = evg::step_occupancy(s->smem, &per_sm)) != cudaSuccess || per_sm < 1) { delete s; return cuda_fail(e, "occupancy query"); }
+    if ((e = evg::step_occupancy(t, s->smem, &per_sm)) != cudaSuccess || per_sm < 1) { delete s; return cuda_fail(e, "occupancy query"); }
     // persistent CTAs: a whole number of resident waves, never more CTAs than matches need
     const int64_t need = (n_envs + evg::kWarpsPerBlock - 1) / evg::kWarpsPerBlock;
     const int64_t resident = (int64_t)prop.multiProcessorCount * per_sm;

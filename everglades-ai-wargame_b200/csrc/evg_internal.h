@@ -41,7 +41,8 @@ struct Tables {
     int32_t turn_limit, capture_bonus, auto_reset, max_group_size;
     int32_t has_small_groups, hist_words, pad0, pad1;  // hist_words: u32 words per side of the damage histogram
     uint32_t seed_lo, seed_hi, env_base, pad2;
-    double max_score;
+    float max_score_f;
+    float pad5;
     // per-warp shared-memory carve-up (bytes)
     int32_t sm_acc, sm_hist, sm_obs, sm_misc, sm_warp_stride, sm_tables_bytes, pad3, pad4;
     double node_def[kNN];
@@ -56,6 +57,7 @@ struct Tables {
     uint8_t ut_damage[EVG_MAX_UNIT_TYPES], ut_speed[EVG_MAX_UNIT_TYPES], ut_control[EVG_MAX_UNIT_TYPES],
         ut_cost[EVG_MAX_UNIT_TYPES];
     uint8_t g_type[kGroupLanes], g_size[kGroupLanes];
+    uint8_t g_damage[kGroupLanes], g_speed[kGroupLanes], g_control[kGroupLanes], g_cost[kGroupLanes];  // per group lane
     uint8_t edge[kNN][kNN];
 };
 
@@ -85,7 +87,7 @@ cudaError_t launch_import(const Tables& t, uint32_t* records, double* health, in
                           const EvgEnvState* in, cudaStream_t stream);
 cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t* actions, int player, int64_t n_envs,
                                 cudaStream_t stream);
-cudaError_t step_occupancy(size_t smem, int* blocks_per_sm);
+cudaError_t step_occupancy(const Tables& t, size_t smem, int* blocks_per_sm);
 cudaError_t set_step_smem(size_t smem);
 
 }  // namespace evg

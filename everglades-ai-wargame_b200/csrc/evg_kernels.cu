@@ -26,11 +26,10 @@ struct WarpSmem {
     uint32_t* acc;   // [2][nn] per (side,node) accumulators
     uint32_t* hist;  // [2][hist_words] damage histogram, 2 x u16 per word
     float* obs;      // [2][obs_len] observation staging
-    uint32_t* res;   // [24] combat result per group: alive mask | avg_health << 16
-    uint16_t* act;   // [14] action rows (gid | nid << 8)
+    double* hs;      // [24] post-combat health sum of each fighting group
+    uint32_t* res;   // [24] post-combat alive mask of each fighting group
+    uint32_t* cmd;   // [24] accepted command per group (action phase) / combat info per group (combat)
     uint8_t* pair;   // [96] (lane | block << 5) draw work list
-    uint8_t* tb;     // [24] histogram base of each fighting group
-    uint8_t* nb;     // [2][nn] histogram base of each (side,node)
 };
 
 __device__ __forceinline__ WarpSmem carve(unsigned char* base, const Tables& S)
@@ -41,11 +40,10 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, const Tables& S)
     W.hist = reinterpret_cast<uint32_t*>(base + S.sm_hist);
     W.obs = reinterpret_cast<float*>(base + S.sm_obs);
     unsigned char* m = base + S.sm_misc;
-    W.res = reinterpret_cast<uint32_t*>(m);
-    W.act = reinterpret_cast<uint16_t*>(m + 96);
-    W.pair = m + 128;
-    W.tb = m + 224;
-    W.nb = m + 256;
+    W.hs = reinterpret_cast<double*>(m);
+    W.res = reinterpret_cast<uint32_t*>(m + 192);
+    W.cmd = reinterpret_cast<uint32_t*>(m + 288);
+    W.pair = m + 384;
     return W;
 }
 
@@ -63,21 +61,35 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// Compile-time map size (NODES > 0: DemoMap's 11 is the instantiated fast path) or run-time (0).
+template <int NODES>
+struct Dim {
+    const Tables& S;
+    __device__ __forceinline__ explicit Dim(const Tables& s) : S(s) {}
+    __device__ __forceinline__ int n_nodes() const { return NODES ? NODES : S.n_nodes; }
+    __device__ __forceinline__ int nn() const { return n_nodes() + 1; }
+    __device__ __forceinline__ int obs_len() const { return 1 + 4 * n_nodes() + 5 * EVG_NUM_GROUPS; }
+    __device__ __forceinline__ int rec_words8() const { return NODES ? ((kRecNode0 + NODES) * 4 + 31) / 32 * 4 : S.rec_words8; }
+};
+
 // Per-(side,node) sums over the groups LISTED at the node (node.groups[pid]: location == node and
 // not destroyed).  One shared-memory atomic per group packs three reductions:
 //   [0:10)  units of all listed groups, moving or not   (board_state opponent count, server.py:446-449)
 //   [10:24) sum count*control of non-moving groups       (capture points, server.py:718-724)
 //   [24:29) number of non-moving groups                  (controllers, server.py:725-726)
+template <int NODES>
 __device__ __forceinline__ void node_accumulate(const Tables& S, const WarpSmem& W, int lane, bool is_grp, int side,
-                                                uint32_t w0, uint32_t w1, int nn)
+                                                uint32_t w0, uint32_t w1)
 {
+    const Dim<NODES> D(S);
+    const int nn = D.nn();
     for (int i = lane; i < 2 * nn; i += 32) W.acc[i] = 0;
     __syncwarp();
     const uint32_t alive = w1 & 0xFFFFu;
     if (is_grp && alive) {
         const uint32_t cnt = __popc(alive);
         uint32_t v = cnt;
-        if (!(w0 & W0_MOVING)) v |= (cnt * S.ut_control[S.g_type[lane]]) << 10 | 1u << 24;
+        if (!(w0 & W0_MOVING)) v |= (cnt * S.g_control[lane]) << 10 | 1u << 24;
         atomicAdd(&W.acc[side * nn + (w0 & W0_LOC_MASK)], v);
     }
     __syncwarp();
@@ -85,15 +97,17 @@ __device__ __forceinline__ void node_accumulate(const Tables& S, const WarpSmem&
 
 // board_state (server.py:382-455) + player_state (server.py:457-501) + concat (env.py:158-171)
 // for both players, staged in shared memory and streamed out as one contiguous row.
+template <int NODES>
 __device__ __forceinline__ void pack_obs(const Tables& S, const WarpSmem& W, int lane, bool is_grp, int side, int gid,
-                                         uint32_t w0, uint32_t w1, uint32_t nw, uint32_t turn, int nn, float* out)
+                                         uint32_t w0, uint32_t w1, uint32_t nw, uint32_t turn, float* out)
 {
-    const int L = S.obs_len;
+    const Dim<NODES> D(S);
+    const int L = D.obs_len(), nn = D.nn();
     if (lane == 0) {
         W.obs[0] = (float)turn;
         W.obs[L] = (float)turn;
     }
-    if (lane < S.n_nodes) {
+    if (lane < D.n_nodes()) {
         const int n = lane + 1;
         const uint32_t f = S.node_flags[n];
         const float fd = (float)(f & 1u), fo = (float)((f >> 1) & 1u);
@@ -104,7 +118,7 @@ __device__ __forceinline__ void pack_obs(const Tables& S, const WarpSmem& W, int
         o1[0] = fd; o1[1] = fo; o1[2] = cs; o1[3] = (float)(W.acc[n] & 1023u);
     }
     if (is_grp) {
-        float* o = W.obs + side * L + 1 + 4 * S.n_nodes + 5 * gid;
+        float* o = W.obs + side * L + 1 + 4 * D.n_nodes() + 5 * gid;
         const uint32_t loc = w0 & W0_LOC_MASK;
         o[0] = (float)(side ? (uint32_t)S.p1_map[loc] : loc);
         o[1] = (float)S.g_type[lane];
@@ -115,24 +129,29 @@ __device__ __forceinline__ void pack_obs(const Tables& S, const WarpSmem& W, int
     __syncwarp();
     float2* o2 = reinterpret_cast<float2*>(out);  // 2*obs_len floats per match: always 8-byte aligned
     const float2* s2 = reinterpret_cast<const float2*>(W.obs);
+#pragma unroll 4
     for (int i = lane; i < L; i += 32) __stcs(o2 + i, s2[i]);
     __syncwarp();
 }
 
 // numpy's float64 pairwise sum (np.sum at server.py:481) of the `size` unit slots held one per lane
 // in a 16-lane half-warp (slots >= size and dead units hold 0.0, which adds exactly).
-__device__ __forceinline__ double half_pairwise_sum(const Tables& S, double h, int size, int u, int half)
+__device__ __forceinline__ double half_pairwise_sum(const Tables& S, double h, int size)
 {
     double v = h;
-    const double up = __shfl_down_sync(FULL, h, 8, 16);
-    if (size == 16) v = __dadd_rn(h, up);  // n == 16: r[k] = a[k] + a[8+k] before the tree
+    if (S.max_group_size == 16) {  // n == 16: r[k] = a[k] + a[8+k] before the tree
+        const double up = __shfl_down_sync(FULL, h, 8, 16);
+        if (size == 16) v = __dadd_rn(h, up);
+    }
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1, 16));
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2, 16));
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 4, 16));
     double res = v;  // lanes 0..7: ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7))
-    for (int i = 8; i < S.max_group_size && i < 16; ++i) {
-        const double x = __shfl_sync(FULL, h, i, 16);
-        if (size < 16 && i < size) res = __dadd_rn(res, x);  // remainder added sequentially
+    if (__any_sync(FULL, size > 8 && size < 16)) {  // remainder a[8..n-1] added sequentially
+        for (int i = 8; i < S.max_group_size && i < 15; ++i) {
+            const double x = __shfl_sync(FULL, h, i, 16);
+            if (size < 16 && i < size) res = __dadd_rn(res, x);
+        }
     }
     if (S.has_small_groups) {  // n < 8: plain left-to-right loop from 0.0
         double seq = 0.0;
@@ -142,56 +161,61 @@ __device__ __forceinline__ double half_pairwise_sum(const Tables& S, double h, i
         }
         if (size < 8) res = seq;
     }
-    (void)u; (void)half;
     return res;
 }
 
 // ---------------------------------------------------------------------------------------------
 // One turn of one match by one warp: env.py:32-73 step -> server.py:211-279 game_turn.
 // ---------------------------------------------------------------------------------------------
+template <int NODES>
 __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, const StepArgs& A, int64_t env, int lane,
                                            unsigned long long* cta_stats)
 {
-    const int nn = S.n_nodes + 1;
+    const Dim<NODES> D(S);
+    const int n_nodes = D.n_nodes(), nn = D.nn(), rec_words8 = D.rec_words8();
     const bool is_grp = lane < kGroupLanes;
     const int side = lane >= EVG_NUM_GROUPS ? 1 : 0;
     const int gid = lane - side * EVG_NUM_GROUPS;
 
-    // ---- load the resident record (coalesced 8-byte per lane) and this turn's action rows
-    uint2* grec = reinterpret_cast<uint2*>(A.records) + env * S.rec_words8;
+    // ---- load the resident record (one coalesced 8-byte access per lane) and this turn's action rows
+    uint2* grec = reinterpret_cast<uint2*>(A.records) + env * rec_words8;
     uint2* srec2 = reinterpret_cast<uint2*>(W.rec);
-    for (int i = lane; i < S.rec_words8; i += 32) srec2[i] = grec[i];
-    if (lane < 2 * EVG_MAX_ACTIONS)
-        W.act[lane] = reinterpret_cast<const uint16_t*>(A.actions)[env * (2 * EVG_MAX_ACTIONS) + lane];
+    uint2 own = make_uint2(0u, 0u);
+    if (lane < rec_words8) own = grec[lane];
+    uint32_t arow = 0;
+    if (lane < 2 * EVG_MAX_ACTIONS) arow = reinterpret_cast<const uint16_t*>(A.actions)[env * (2 * EVG_MAX_ACTIONS) + lane];
+    if (lane < rec_words8) srec2[lane] = own;
+    for (int i = lane + 32; i < rec_words8; i += 32) srec2[i] = grec[i];
+    if (is_grp) W.cmd[lane] = 0xFFFFFFFFu;
     __syncwarp();
-    uint32_t w0 = is_grp ? W.rec[2 * lane] : 0u, w1 = is_grp ? W.rec[2 * lane + 1] : 0u;
-    uint32_t nw = lane < S.n_nodes ? W.rec[kRecNode0 + lane] : 0u;
-    uint32_t turn = W.rec[kRecTurn] + 1u;  // server.py:214
-    uint32_t episode = W.rec[kRecEpisode];
-    const int gtype = is_grp ? S.g_type[lane] : 0;
+    uint32_t w0 = is_grp ? own.x : 0u, w1 = is_grp ? own.y : 0u;  // uint2 L = words 2L, 2L+1 = group lane L
+    uint32_t nw = lane < n_nodes ? W.rec[kRecNode0 + lane] : 0u;
+    uint32_t turn = __shfl_sync(FULL, own.x, kRecTurn / 2) + 1u;  // server.py:214
+    uint32_t episode = __shfl_sync(FULL, own.y, kRecTurn / 2);
 
-    // ---- action decode + validation, server.py:218-271.  Each group lane scans its player's 7 rows
-    // and takes the first that names it and passes (t2) not moving, (t3) destination adjacent; a
-    // row that fails does not consume the group's one command per turn (t1 only sees accepted rows).
-    if (is_grp && !(w0 & W0_MOVING)) {
-        const uint32_t loc = w0 & W0_LOC_MASK;
-        bool taken = false;
-#pragma unroll
-        for (int i = 0; i < EVG_MAX_ACTIONS; ++i) {
-            const uint32_t a = W.act[side * EVG_MAX_ACTIONS + i];
-            const int ag = (int)(int8_t)(a & 0xFFu);
-            int an = (int)(int8_t)(a >> 8);
-            if (!taken && ag == gid) {
-                an = (an >= 0 && an <= S.n_nodes) ? an : 0;
-                if (side) an = S.p1_map[an];  // server.py:233-234
-                const uint32_t d = S.edge[loc][an];
-                if (d) {  // server.py:267-270
-                    taken = true;
-                    w0 = (w0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | (uint32_t)an << W0_DEST_SHIFT |
-                         d << W0_DIST_SHIFT | W0_READY;
-                }
-            }
+    // ---- action decode + validation, server.py:218-271.  One lane per action row (player = lane/7):
+    // a row is valid if (t2) the group is not moving and (t3) the destination is adjacent; of the valid
+    // rows naming one group the FIRST wins (t1 only ever sees accepted rows) = shared-memory atomicMin
+    // on (row index, destination, distance).
+    if (lane < 2 * EVG_MAX_ACTIONS) {
+        const int ag = (int)(int8_t)(arow & 0xFFu);
+        int an = (int)(int8_t)(arow >> 8);
+        const int pl = lane >= EVG_MAX_ACTIONS ? 1 : 0;
+        if ((unsigned)ag < (unsigned)EVG_NUM_GROUPS) {
+            an = (unsigned)an <= (unsigned)n_nodes ? an : 0;
+            if (pl) an = S.p1_map[an];  // server.py:233-234
+            const int L = pl * EVG_NUM_GROUPS + ag;
+            const uint32_t gw0 = W.rec[2 * L];
+            const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
+            if (d && !(gw0 & W0_MOVING)) atomicMin(&W.cmd[L], (uint32_t)lane << 16 | (uint32_t)an << 8 | d);
         }
+    }
+    __syncwarp();
+    if (is_grp) {
+        const uint32_t c = W.cmd[lane];
+        if (c != 0xFFFFFFFFu)  // server.py:267-270
+            w0 = (w0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | ((c >> 8) & 0x3Fu) << W0_DEST_SHIFT |
+                 (c & 0xFFu) << W0_DIST_SHIFT | W0_READY;
     }
 
     // ---- combat, server.py:503-654
@@ -200,37 +224,36 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
         const uint32_t cnt = __popc(alive);
         const uint32_t loc = w0 & W0_LOC_MASK;
         const bool present = is_grp && alive && !(w0 & W0_MOVING);  // listed and not in transit (:523-530)
-        for (int i = lane; i < 2 * nn; i += 32) W.acc[i] = 0;
-        __syncwarp();
-        if (present) atomicAdd(&W.acc[side * nn + loc], cnt);  // counts[player] summed per node
-        __syncwarp();
-        const bool fighting = present && W.acc[(1 - side) * nn + loc] != 0;  // both players present (:539)
+        // a node is contested when both players have a present group there (:539)
+        const uint32_t peers = __match_any_sync(FULL, present ? loc : 64u + (uint32_t)lane);
+        const bool fighting = present && (peers & (side ? 0x00000FFFu : 0x00FFF000u)) != 0;
         const uint32_t fmask = __ballot_sync(FULL, fighting);
         if (fmask) {
-            // Histogram slot of a target = (position of its group among the side's fighting groups
-            // ordered by node, then node-list order) + alive rank in the group.  Within one node that
+            // Histogram slot of a target = (units of its side's fighting groups that sort before its
+            // group by node, then node-list order) + alive rank inside the group.  Inside one node that
             // is exactly the uid the reference draws (uid -> (group, r-th unit alive
-            // before combat) is fixed before any damage lands).
+            // before combat) is fixed before any damage lands).  One pass over the fighting groups
+            // gives every group: tb = its own histogram base, hb = the base of the OPPOSING side at
+            // its node, n = opposing alive units at its node (np.sum(counts[opp_pid]), :552).
             const uint32_t arrival = w1 >> 16;
             const uint32_t key = (uint32_t)side << 31 | loc << 25 | arrival << 9 | (uint32_t)gid << 5 | cnt;
-            uint32_t tbase = 0;
-            bool first = true;
+            uint32_t tb = 0, hb = 0, n = 0;
             for (uint32_t m = fmask; m; m &= m - 1) {
                 const uint32_t ok = __shfl_sync(FULL, key, __ffs(m) - 1);
-                if (((ok ^ key) >> 31) == 0 && ok < key) {
-                    tbase += ok & 31u;
-                    if (((ok ^ key) >> 25) == 0) first = false;
+                const uint32_t oc = ok & 31u, oloc = (ok >> 25) & 63u;
+                if ((ok ^ key) >> 31) {  // opposing side
+                    if (oloc < loc) hb += oc;
+                    else if (oloc == loc) n += oc;
+                } else if (ok < key) {
+                    tb += oc;
                 }
             }
             for (int i = lane; i < 2 * S.hist_words; i += 32) W.hist[i] = 0;
-            if (fighting) {
-                W.tb[lane] = (uint8_t)tbase;
-                if (first) W.nb[side * nn + loc] = (uint8_t)tbase;
-            }
+            if (fighting) W.cmd[lane] = tb | hb << 8 | n << 16;
             // work list of (group, block of 4 attackers)
             const uint32_t nblk = fighting ? (cnt + 3) >> 2 : 0;
-            const uint32_t b1 = __ballot_sync(FULL, nblk >= 1), b2 = __ballot_sync(FULL, nblk >= 2),
-                           b3 = __ballot_sync(FULL, nblk >= 3), b4 = __ballot_sync(FULL, nblk >= 4);
+            const uint32_t b1 = fmask, b2 = __ballot_sync(FULL, nblk >= 2), b3 = __ballot_sync(FULL, nblk >= 3),
+                           b4 = __ballot_sync(FULL, nblk >= 4);
             const uint32_t lt = (1u << lane) - 1u;
             const int o1 = __popc(b1), o2 = o1 + __popc(b2), o3 = o2 + __popc(b3), npairs = o3 + __popc(b4);
             if (nblk >= 1) W.pair[__popc(b1 & lt)] = (uint8_t)lane;
@@ -248,9 +271,9 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                     const int gs = L >= EVG_NUM_GROUPS ? 1 : 0, gg = L - gs * EVG_NUM_GROUPS;
                     const uint32_t gl = W.rec[2 * L] & W0_LOC_MASK;  // loc/alive untouched since the load
                     const int gcnt = __popc(W.rec[2 * L + 1] & 0xFFFFu);
-                    const uint32_t n = W.acc[(1 - gs) * nn + gl];
-                    const uint32_t hb = W.nb[(1 - gs) * nn + gl];
-                    const uint32_t dmg = S.ut_damage[S.g_type[L]];
+                    const uint32_t info = W.cmd[L];
+                    const uint32_t gn = info >> 16, ghb = (info >> 8) & 0xFFu;
+                    const uint32_t dmg = S.g_damage[L];
                     uint32_t r[4];
                     philox4x32_10(S.env_base + (uint32_t)env, turn, gl | (uint32_t)gs << 8 | (uint32_t)gg << 16 | (uint32_t)k << 24,
                                   episode << 8, S.seed_lo, S.seed_hi, r);
@@ -258,7 +281,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (4 * k + q < gcnt) {
-                            const uint32_t idx = hb + __umulhi(r[q], n);
+                            const uint32_t idx = ghb + __umulhi(r[q], gn);
                             atomicAdd(&hist[idx >> 1], dmg << ((idx & 1u) * 16));
                         }
                 }
@@ -278,13 +301,13 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                 const uint32_t gw0 = W.rec[2 * Ls], gw1 = W.rec[2 * Ls + 1];
                 const uint32_t gl = gw0 & W0_LOC_MASK;
                 const uint32_t galive = act ? gw1 & 0xFFFFu : 0u;
-                const int gsize = S.g_size[Ls], gt = S.g_type[Ls];
+                const int gsize = S.g_size[Ls];
                 const bool mine = (galive >> u) & 1u;
                 double* hp = A.health + env * S.health_slots + S.g_slot[Ls] + u;
                 double h = 0.0;
                 uint32_t d = 0;
                 if (mine) {
-                    const uint32_t idx = (uint32_t)W.tb[Ls] + __popc(galive & ((1u << u) - 1u));
+                    const uint32_t idx = (W.cmd[Ls] & 0xFFu) + __popc(galive & ((1u << u) - 1u));
                     d = (W.hist[gs * S.hist_words + (idx >> 1)] >> ((idx & 1u) * 16)) & 0xFFFFu;
                     h = *hp;
                 }
@@ -295,7 +318,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                     const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
                     const int bonus = (cb == gs ? 1 : 0) + ((S.node_flags[gl] >> 2) & 1);
                     const double node_def = __dmul_rn((double)bonus, S.node_def[gl]);
-                    const double loss = __ddiv_rn(__dmul_rn(10.0, (double)d), __dadd_rn(S.unit_armor[gt], node_def));
+                    const double loss = __ddiv_rn(__dmul_rn(10.0, (double)d), __dadd_rn(S.unit_armor[S.g_type[Ls]], node_def));
                     h = __dsub_rn(h, loss);  // server.py:609
                     if (h <= 0.0) {          // server.py:615-618
                         h = 0.0;
@@ -304,19 +327,19 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                     *hp = h;
                 }
                 const uint32_t deadmask = (__ballot_sync(FULL, dead) >> (16 * half)) & 0xFFFFu;
-                const uint32_t nalive = galive & ~deadmask;
-                const double hsum = half_pairwise_sum(S, h, gsize, u, half);
+                const double hsum = half_pairwise_sum(S, h, gsize);
                 if (act && u == 0) {
-                    // player_state's int((health*1.)/units_alive), server.py:491
-                    const int avg = nalive ? (int)__ddiv_rn(hsum, (double)__popc(nalive)) : 0;
-                    W.res[Ls] = nalive | (uint32_t)avg << 16;
+                    W.res[Ls] = galive & ~deadmask;
+                    W.hs[Ls] = hsum;
                 }
             }
             __syncwarp();
             if (fighting) {
-                const uint32_t r = W.res[lane];
-                w1 = (w1 & 0xFFFF0000u) | (r & 0xFFFFu);  // alive == 0: destroyed, leaves the node list (:623-627)
-                w0 = (w0 & ~(127u << W0_AVG_SHIFT)) | ((r >> 16) & 127u) << W0_AVG_SHIFT;
+                const uint32_t nalive = W.res[lane];
+                // player_state's int((health*1.)/units_alive), server.py:491 — one division for all groups
+                const int avg = nalive ? (int)__ddiv_rn(W.hs[lane], (double)__popc(nalive)) : 0;
+                w1 = (w1 & 0xFFFF0000u) | nalive;  // alive == 0: destroyed, leaves the node list (:623-627)
+                w0 = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
             }
         }
     }
@@ -326,7 +349,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
         if (w0 & W0_READY) {
             w0 = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
         } else if (w0 & W0_MOVING) {
-            int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.ut_speed[gtype];  // :671
+            int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[lane];  // :671
             if (dist <= 0) {  // arrived: appended to the destination's list (:678-695)
                 const uint32_t dest = (w0 >> W0_DEST_SHIFT) & 0x3Fu;
                 w0 = (w0 & (127u << W0_AVG_SHIFT)) | dest;
@@ -338,10 +361,10 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
     }
 
     // ---- capture, server.py:708-767 (current_turn > 0 here; the turn-0 case is the reset kernel's)
-    node_accumulate(S, W, lane, is_grp, side, w0, w1, nn);
+    node_accumulate<NODES>(S, W, lane, is_grp, side, w0, w1);
     int s0 = 0, s1 = 0;
     bool basecap = false;
-    if (lane < S.n_nodes) {
+    if (lane < n_nodes) {
         const int n = lane + 1;
         int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
         const uint32_t a0 = W.acc[n], a1 = W.acc[nn + n];
@@ -375,7 +398,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
     }
     const uint32_t galive_now = w1 & 0xFFFFu;
     if (is_grp && galive_now) {  // server.py:313-317
-        const int v = __popc(galive_now) * (int)S.ut_cost[gtype];
+        const int v = __popc(galive_now) * (int)S.g_cost[lane];
         if (side) s1 += v; else s0 += v;
     }
     s0 = __reduce_add_sync(FULL, s0);
@@ -388,12 +411,13 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
     else if (any_basecap) status = EVG_STATUS_BASE_CAPTURE;
     const bool done = status != 0;
 
-    // ---- reward / done, env.py:37-60
+    // ---- reward / done, env.py:37-60.  float32(float64(score)/MAX_SCORE) == float32 IEEE division for
+    // every score < 2^24 (no double-rounding case exists; checked exhaustively in tests/test_tape.py).
     if (lane < 2) {
         const int mine = lane ? s1 : s0, other = lane ? s0 : s1;
         float r;
         if (done) r = mine == other ? 0.f : (mine > other ? 1.f : (lane ? -1.f : 0.f));
-        else r = (float)__ddiv_rn((double)mine, S.max_score);
+        else r = __fdiv_rn((float)mine, S.max_score_f);
         A.reward[env * 2 + lane] = r;
         if (A.scores) A.scores[env * 2 + lane] = mine;
     }
@@ -403,8 +427,8 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
     }
 
     // ---- observations of the post-turn state
-    float* obs_out = A.obs + env * 2 * S.obs_len;
-    pack_obs(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, nn, obs_out);
+    float* obs_out = A.obs + env * 2 * D.obs_len();
+    pack_obs<NODES>(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, obs_out);
 
     // ---- termination with in-place auto-reset
     if (done && S.auto_reset != EVG_AUTORESET_OFF) {
@@ -417,23 +441,23 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
             atomicAdd(&cta_stats[ST_STATUS0 + status], 1ull);
         }
         if (is_grp) { w0 = S.init_w0[lane]; w1 = S.init_w1[lane]; }
-        if (lane < S.n_nodes) nw = S.init_node[lane + 1];
+        if (lane < n_nodes) nw = S.init_node[lane + 1];
         turn = 0;
         episode += 1;
         double* hp = A.health + env * S.health_slots;
         for (int i = lane; i < S.health_slots; i += 32) hp[i] = 100.0;  // definitions.py:62
         if (S.auto_reset == EVG_AUTORESET_NEXT) {
-            node_accumulate(S, W, lane, is_grp, side, w0, w1, nn);
-            pack_obs(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, nn, obs_out);
+            node_accumulate<NODES>(S, W, lane, is_grp, side, w0, w1);
+            pack_obs<NODES>(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, obs_out);
         }
     }
 
     // ---- store the record
-    if (is_grp) { W.rec[2 * lane] = w0; W.rec[2 * lane + 1] = w1; }
-    if (lane < S.n_nodes) W.rec[kRecNode0 + lane] = nw;
-    if (lane == 0) { W.rec[kRecTurn] = turn; W.rec[kRecEpisode] = episode; }
+    if (is_grp) srec2[lane] = make_uint2(w0, w1);
+    if (lane < n_nodes) W.rec[kRecNode0 + lane] = nw;
+    if (lane == 0) srec2[kRecTurn / 2] = make_uint2(turn, episode);
     __syncwarp();
-    for (int i = lane; i < S.rec_words8; i += 32) grec[i] = srec2[i];
+    for (int i = lane; i < rec_words8; i += 32) grec[i] = srec2[i];
     __syncwarp();
 }
 
@@ -445,6 +469,7 @@ __device__ __forceinline__ const Tables& stage_tables(const Tables& T, unsigned 
     return *reinterpret_cast<const Tables*>(smem);
 }
 
+template <int NODES>
 __global__ void __launch_bounds__(kThreads) evg_step_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -455,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) evg_step_kernel(const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const WarpSmem W = carve(smem + T.sm_tables_bytes + 128 + warp * T.sm_warp_stride, S);
     for (int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + warp; env < A.n_envs; env += (int64_t)gridDim.x * kWarpsPerBlock)
-        step_match(S, W, A, env, lane, cta_stats);
+        step_match<NODES>(S, W, A, env, lane, cta_stats);
     __syncthreads();
     if (threadIdx.x < ST_COUNT && cta_stats[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], cta_stats[threadIdx.x]);
 }
@@ -472,7 +497,6 @@ __global__ void __launch_bounds__(kThreads) evg_reset_kernel(const __grid_consta
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const WarpSmem W = carve(smem + T.sm_tables_bytes + 128 + warp * T.sm_warp_stride, S);
-    const int nn = S.n_nodes + 1;
     const bool is_grp = lane < kGroupLanes;
     const int side = lane >= EVG_NUM_GROUPS ? 1 : 0, gid = lane - side * EVG_NUM_GROUPS;
     for (int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + warp; env < n_envs; env += (int64_t)gridDim.x * kWarpsPerBlock) {
@@ -492,8 +516,8 @@ __global__ void __launch_bounds__(kThreads) evg_reset_kernel(const __grid_consta
         double* hp = health + env * S.health_slots;
         for (int i = lane; i < S.health_slots; i += 32) hp[i] = 100.0;
         if (obs) {
-            node_accumulate(S, W, lane, is_grp, side, w0, w1, nn);
-            pack_obs(S, W, lane, is_grp, side, gid, w0, w1, nw, 0u, nn, obs + env * 2 * S.obs_len);
+            node_accumulate<0>(S, W, lane, is_grp, side, w0, w1);
+            pack_obs<0>(S, W, lane, is_grp, side, gid, w0, w1, nw, 0u, obs + env * 2 * S.obs_len);
         }
     }
 }
@@ -637,21 +661,27 @@ __global__ void evg_agent_random_kernel(const __grid_constant__ Tables T, const 
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// DemoMap's node count gets a compile-time instantiation; any other map runs the generic one.
+constexpr int kFastNodes = 11;
+
 cudaError_t set_step_smem(size_t smem)
 {
-    cudaError_t e = cudaFuncSetAttribute(evg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(evg_step_kernel<kFastNodes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(evg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-cudaError_t step_occupancy(size_t smem, int* blocks_per_sm)
+cudaError_t step_occupancy(const Tables& t, size_t smem, int* blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_kernel, kThreads, smem);
+    if (t.n_nodes == kFastNodes) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_kernel<kFastNodes>, kThreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_kernel<0>, kThreads, smem);
 }
 
 cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t smem, cudaStream_t stream)
 {
-    evg_step_kernel<<<grid, kThreads, smem, stream>>>(t, a);
+    if (t.n_nodes == kFastNodes) evg_step_kernel<kFastNodes><<<grid, kThreads, smem, stream>>>(t, a);
+    else evg_step_kernel<0><<<grid, kThreads, smem, stream>>>(t, a);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,61 @@
+"""Config generality: other maps, unit tables, budgets and GameSetup values must stay
+bit-exact with the oracle — including group sizes that hit every branch of numpy's pairwise sum
+(n < 8, 8 <= n < 16 with a remainder, n == 16) and the 'DEFEND' fortress bonus DemoMap never enables."""
+import json
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import adjacent_actions, assert_states_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def write_configs(tmp_path, budget, turn_limit=60, bonus=300):
+    nodes = []
+    edges = {1: [(2, 2), (3, 5)], 2: [(1, 2), (3, 3), (4, 1)], 3: [(1, 5), (2, 3), (4, 2), (5, 3)], 4: [(2, 1), (3, 2), (5, 2), (6, 4)],
+             5: [(3, 3), (4, 2), (6, 2), (7, 5)], 6: [(4, 4), (5, 2), (7, 2)], 7: [(5, 5), (6, 2)]}
+    res = {2: ["DEFEND"], 6: ["DEFEND", "OBSERVE"], 4: ["DEFENSE"], 3: ["OBSERVE"]}
+    for i in range(1, 8):
+        nodes.append({"ID": i, "Connections": [{"ConnectedID": d, "Distance": w} for d, w in edges[i]],
+                      "ControlPoints": 250 if i in (1, 7) else 60 + 10 * i, "Resource": res.get(i, []),
+                      "StructureDefense": [0, 1, 1.25, 2, 1.5, 1.75, 0.5, 3][i], "TeamStart": {1: 0, 7: 1}.get(i, -1)})
+    (tmp_path / "Map7.json").write_text(json.dumps({"MapName": "seven", "nodes": nodes, "P1NodeMap": [0, 7, 6, 5, 4, 3, 2, 1]}))
+    units = [{"Name": "Tank", "Health": 4, "Damage": 2, "Speed": 1, "Control": 1, "Cost": 3},
+             {"Name": "Scout", "Health": 0.5, "Damage": 1, "Speed": 3, "Control": 0, "Cost": 1},
+             {"Name": "Controller", "Health": 2.5, "Damage": 1, "Speed": 2, "Control": 3, "Cost": 2},
+             {"Name": "Striker", "Health": 1, "Damage": 5, "Speed": 2, "Control": 1, "Cost": 2}]
+    (tmp_path / "Units4.json").write_text(json.dumps({"units": units}))
+    (tmp_path / "Setup.json").write_text(json.dumps({"TurnLimit": turn_limit, "CaptureBonus": bonus, "UnitBudget": budget}))
+    return str(tmp_path)
+
+
+@pytest.mark.parametrize("budget", [60, 100, 120, 180, 192, 12])
+def test_other_map_units_and_budgets(tmp_path, budget):
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+    from oracle import evg_oracle as eo
+
+    d = write_configs(tmp_path, budget)
+    cfg = evgsim.load_config(d, "Map7.json", "Units4.json", "Setup.json", auto_reset=1)
+    assert cfg.n_nodes == 7 and cfg.turn_limit == 60
+    n = 768
+    env = evgsim.BatchedEvergladesEnv(n, seed=budget, config=cfg, auto_reset=1, env_id_offset=9)
+    ora = eo.OracleBatch(cfg, n, seed=budget, first=9)
+    assert env.obs_len == 1 + 4 * 7 + 60
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
+    rng = np.random.default_rng(budget)
+    deaths = 0
+    for t in range(150):
+        acts = adjacent_actions(rng, ora.states, cfg)
+        obs, rew, done, info = env.step(acts)
+        oobs, orew, odone = ora.step(acts)
+        assert np.array_equal(done.cpu().numpy(), odone), t
+        assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+        assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
+        deaths += int((ora.states["groups"]["destroyed"]).sum())
+        if t % 25 == 24:
+            assert_states_equal(env.get_state(), ora.states, "turn %d" % (t + 1))
+    assert deaths > 0  # the scenario really fights
+    assert env.episode_stats()["episodes"] >= 2 * n

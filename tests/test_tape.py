@@ -49,3 +49,14 @@ def test_draw_is_in_range_and_uses_all_lanes():
             assert 0 <= tape.combat_draw(7, 3, 10, 5, 1, 11, j, n) < n
     assert len(seen) == 12
     assert tape.combat_word(7, 3, 10, 5, 1, 11, 0, episode=1) != tape.combat_word(7, 3, 10, 5, 1, 11, 0)
+
+
+def test_reward_float32_division_has_no_double_rounding():
+    """The kernel computes the non-terminal reward (env.py:58-60, float64 score/3700) as ONE float32 IEEE
+    division.  float32(float64(s)/D) == float32(s)/float32(D) for every score s < 2^24: the exact
+    quotient can never sit within a float64 half-ulp of a float32 rounding midpoint unless it is on it."""
+    s = np.arange(0, 1 << 24, dtype=np.int64)
+    for D in (3700, 1, 7, 2999):
+        a = (s.astype(np.float64) / float(D)).astype(np.float32)
+        b = s.astype(np.float32) / np.float32(D)
+        assert np.array_equal(a, b), D
