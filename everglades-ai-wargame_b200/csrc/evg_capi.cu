@@ -102,7 +102,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
         t.ut_control[k] = (uint8_t)c.unit_control[k];
         t.ut_cost[k] = (uint8_t)c.unit_cost[k];
     }
-    int max_units = 0, max_size = 0, small = 0, per_player_slots = 0;
+    int max_units = 0, max_size = 0, small = 0, per_player_slots = 0, n_big = 0;
     for (int p = 0; p < EVG_NUM_PLAYERS; ++p) {
         int slots = 0, units = 0;
         for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
@@ -111,6 +111,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
             if (type >= c.n_unit_types) return fail(EVG_E_CONFIG, "group %d of player %d has unknown unit type %d", g, p, type);
             t.g_type[L] = (uint8_t)type;
             t.g_size[L] = (uint8_t)size;
+            t.g_big[L] = size > 8 ? (uint8_t)n_big++ : (uint8_t)0;
             t.g_damage[L] = t.ut_damage[type];
             t.g_speed[L] = t.ut_speed[type];
             t.g_control[L] = t.ut_control[type];
@@ -130,6 +131,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.health_slots = 2 * per_player_slots;
     t.max_group_size = max_size;
     t.has_small_groups = small;
+    t.n_big = n_big;
     t.hist_words = (max_units + 1) / 2 + 1;
     // node state after game_init's capture() at turn 0 (server.py:206,744-745,763-765)
     for (int n = 1; n <= c.n_nodes; ++n) {
@@ -150,7 +152,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.sm_hist = t.sm_acc + round_up(2 * nn * 4, 16);
     t.sm_obs = t.sm_hist + round_up(2 * t.hist_words * 4, 16);
     t.sm_misc = t.sm_obs + round_up(2 * t.obs_len * 4, 16);
-    t.sm_warp_stride = t.sm_misc + 480;
+    t.sm_warp_stride = t.sm_misc + 528 + n_big * 16 * 8;
     t.sm_tables_bytes = round_up((int)sizeof(evg::Tables), 16);
     *out = t;
     return EVG_OK;

@@ -39,7 +39,7 @@ constexpr int W0_AVG_SHIFT = 24;
 struct Tables {
     int32_t n_nodes, obs_len, rec_words8, health_slots;
     int32_t turn_limit, capture_bonus, auto_reset, max_group_size;
-    int32_t has_small_groups, hist_words, pad0, pad1;  // hist_words: u32 words per side of the damage histogram
+    int32_t has_small_groups, hist_words, n_big, pad1;  // hist_words: u32 words per side of the damage histogram
     uint32_t seed_lo, seed_hi, env_base, pad2;
     float max_score_f;
     float pad5;
@@ -57,6 +57,7 @@ struct Tables {
     uint8_t ut_damage[EVG_MAX_UNIT_TYPES], ut_speed[EVG_MAX_UNIT_TYPES], ut_control[EVG_MAX_UNIT_TYPES],
         ut_cost[EVG_MAX_UNIT_TYPES];
     uint8_t g_type[kGroupLanes], g_size[kGroupLanes];
+    uint8_t g_big[kGroupLanes];  // ordinal among the groups with more than 8 units (index into the hbig scratch)
     uint8_t g_damage[kGroupLanes], g_speed[kGroupLanes], g_control[kGroupLanes], g_cost[kGroupLanes];  // per group lane
     uint8_t edge[kNN][kNN];
 };

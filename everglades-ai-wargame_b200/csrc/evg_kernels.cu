@@ -30,6 +30,8 @@ struct WarpSmem {
     uint32_t* res;   // [24] post-combat alive mask of each fighting group
     uint32_t* cmd;   // [24] accepted command per group (action phase) / combat info per group (combat)
     uint8_t* pair;   // [96] (lane | block << 5) draw work list
+    uint8_t* seg;    // [48] (lane | segment << 5) apply work list
+    double* hbig;    // [n_big][16] post-combat unit healths of groups with more than 8 units
 };
 
 __device__ __forceinline__ WarpSmem carve(unsigned char* base, const Tables& S)
@@ -44,6 +46,8 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, const Tables& S)
     W.res = reinterpret_cast<uint32_t*>(m + 192);
     W.cmd = reinterpret_cast<uint32_t*>(m + 288);
     W.pair = m + 384;
+    W.seg = m + 480;
+    W.hbig = reinterpret_cast<double*>(m + 528);
     return W;
 }
 
@@ -134,36 +138,6 @@ __device__ __forceinline__ void pack_obs(const Tables& S, const WarpSmem& W, int
     __syncwarp();
 }
 
-// numpy's float64 pairwise sum (np.sum at server.py:481) of the `size` unit slots held one per lane
-// in a 16-lane half-warp (slots >= size and dead units hold 0.0, which adds exactly).
-__device__ __forceinline__ double half_pairwise_sum(const Tables& S, double h, int size)
-{
-    double v = h;
-    if (S.max_group_size == 16) {  // n == 16: r[k] = a[k] + a[8+k] before the tree
-        const double up = __shfl_down_sync(FULL, h, 8, 16);
-        if (size == 16) v = __dadd_rn(h, up);
-    }
-    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1, 16));
-    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2, 16));
-    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 4, 16));
-    double res = v;  // lanes 0..7: ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7))
-    if (__any_sync(FULL, size > 8 && size < 16)) {  // remainder a[8..n-1] added sequentially
-        for (int i = 8; i < S.max_group_size && i < 15; ++i) {
-            const double x = __shfl_sync(FULL, h, i, 16);
-            if (size < 16 && i < size) res = __dadd_rn(res, x);
-        }
-    }
-    if (S.has_small_groups) {  // n < 8: plain left-to-right loop from 0.0
-        double seq = 0.0;
-        for (int i = 0; i < 7; ++i) {
-            const double x = __shfl_sync(FULL, h, i, 16);
-            if (i < size) seq = __dadd_rn(seq, x);
-        }
-        if (size < 8) res = seq;
-    }
-    return res;
-}
-
 // ---------------------------------------------------------------------------------------------
 // One turn of one match by one warp: env.py:32-73 step -> server.py:211-279 game_turn.
 // ---------------------------------------------------------------------------------------------
@@ -226,40 +200,67 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
         const bool present = is_grp && alive && !(w0 & W0_MOVING);  // listed and not in transit (:523-530)
         // a node is contested when both players have a present group there (:539)
         const uint32_t peers = __match_any_sync(FULL, present ? loc : 64u + (uint32_t)lane);
-        const bool fighting = present && (peers & (side ? 0x00000FFFu : 0x00FFF000u)) != 0;
+        const uint32_t opp_lanes = side ? 0x00000FFFu : 0x00FFF000u;
+        const bool fighting = present && (peers & opp_lanes) != 0;
         const uint32_t fmask = __ballot_sync(FULL, fighting);
         if (fmask) {
-            // Histogram slot of a target = (units of its side's fighting groups that sort before its
-            // group by node, then node-list order) + alive rank inside the group.  Inside one node that
-            // is exactly the uid the reference draws (uid -> (group, r-th unit alive
-            // before combat) is fixed before any damage lands).  One pass over the fighting groups
-            // gives every group: tb = its own histogram base, hb = the base of the OPPOSING side at
-            // its node, n = opposing alive units at its node (np.sum(counts[opp_pid]), :552).
-            const uint32_t arrival = w1 >> 16;
-            const uint32_t key = (uint32_t)side << 31 | loc << 25 | arrival << 9 | (uint32_t)gid << 5 | cnt;
-            uint32_t tb = 0, hb = 0, n = 0;
-            for (uint32_t m = fmask; m; m &= m - 1) {
-                const uint32_t ok = __shfl_sync(FULL, key, __ffs(m) - 1);
-                const uint32_t oc = ok & 31u, oloc = (ok >> 25) & 63u;
-                if ((ok ^ key) >> 31) {  // opposing side
-                    if (oloc < loc) hb += oc;
-                    else if (oloc == loc) n += oc;
-                } else if (ok < key) {
-                    tb += oc;
-                }
+            // Histogram slot of a target = (units of its side's fighting groups at lower-numbered nodes)
+            // + (units of its side's groups listed before it at its node) + alive rank inside the group.
+            // Inside one node that is exactly the uid the reference draws (uid -> (group,
+            // r-th unit alive before combat) is fixed before any damage lands).
+            //   acc[x]      = fighting units at node x, side 0 | side 1 << 16   (np.sum(counts[pid]), :552-553)
+            //   acc[nn + x] = exclusive prefix of acc over nodes = histogram base of (side, x)
+            for (int i = lane; i < nn; i += 32) W.acc[i] = 0;
+            __syncwarp();
+            if (fighting) atomicAdd(&W.acc[loc], cnt << (16 * side));
+            __syncwarp();
+            const uint32_t tot = lane < n_nodes ? W.acc[lane + 1] : 0u;
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                if (NODES && o >= 2 * NODES) break;
+                const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
             }
-            for (int i = lane; i < 2 * S.hist_words; i += 32) W.hist[i] = 0;
-            if (fighting) W.cmd[lane] = tb | hb << 8 | n << 16;
-            // work list of (group, block of 4 attackers)
+            const uint32_t totals = __shfl_sync(FULL, inc, 31);
+            if (lane < n_nodes) W.acc[nn + lane + 1] = inc - tot;
+            const int hw0 = (int)((totals & 0xFFFFu) + 1) >> 1, hw1 = (int)((totals >> 16) + 1) >> 1;
+            for (int i = lane; i < hw0; i += 32) W.hist[i] = 0;
+            for (int i = lane; i < hw1; i += 32) W.hist[S.hist_words + i] = 0;
+            __syncwarp();
+            const uint32_t node_tot = W.acc[loc], node_base = W.acc[nn + loc];
+            const uint32_t n = (node_tot >> (16 * (1 - side))) & 0xFFFFu;    // opposing units at my node
+            const uint32_t hb = (node_base >> (16 * (1 - side))) & 0xFFFFu;  // opposing histogram base
+            uint32_t tb = (node_base >> (16 * side)) & 0xFFFFu;
+            // order inside the node list (node.groups[pid] is in arrival order, then gid)
+            const uint32_t okey = ((w1 >> 16) << 4 | (uint32_t)gid) << 5 | cnt;
+            uint32_t m = fighting ? (peers & ~opp_lanes & ~(1u << lane)) : 0u;
+            while (__any_sync(FULL, m != 0)) {
+                const int src = m ? __ffs(m) - 1 : lane;
+                const uint32_t ok = __shfl_sync(FULL, okey, src);
+                if (m && ok < okey) tb += ok & 31u;
+                m &= m - 1;
+            }
+            if (fighting) {
+                W.cmd[lane] = tb | hb << 8 | n << 16;
+                W.res[lane] = alive;
+            }
+            // work lists: (group, block of 4 attackers) for the draws, (group, 8-slot segment) for the apply
             const uint32_t nblk = fighting ? (cnt + 3) >> 2 : 0;
             const uint32_t b1 = fmask, b2 = __ballot_sync(FULL, nblk >= 2), b3 = __ballot_sync(FULL, nblk >= 3),
                            b4 = __ballot_sync(FULL, nblk >= 4);
+            const uint32_t big = __ballot_sync(FULL, fighting && S.g_size[lane] > 8);
             const uint32_t lt = (1u << lane) - 1u;
             const int o1 = __popc(b1), o2 = o1 + __popc(b2), o3 = o2 + __popc(b3), npairs = o3 + __popc(b4);
-            if (nblk >= 1) W.pair[__popc(b1 & lt)] = (uint8_t)lane;
+            const int nsegs = o1 + __popc(big);
+            if (nblk >= 1) {
+                W.pair[__popc(b1 & lt)] = (uint8_t)lane;
+                W.seg[__popc(b1 & lt)] = (uint8_t)lane;
+            }
             if (nblk >= 2) W.pair[o1 + __popc(b2 & lt)] = (uint8_t)(lane | 1 << 5);
             if (nblk >= 3) W.pair[o2 + __popc(b3 & lt)] = (uint8_t)(lane | 2 << 5);
             if (nblk >= 4) W.pair[o3 + __popc(b4 & lt)] = (uint8_t)(lane | 3 << 5);
+            if ((big >> lane) & 1u) W.seg[o1 + __popc(big & lt)] = (uint8_t)(lane | 1 << 5);
             __syncwarp();
             // draws: every alive unit of a fighting group targets uid = randint(opposing alive units
             // at the node) and adds its type's damage to infliction[uid], server.py:549-566
@@ -287,38 +288,36 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                 }
             }
             __syncwarp();
-            // apply: two target groups per pass, one unit slot per lane of a half-warp; server.py:573-643
-            const int half = lane >> 4, u = lane & 15;
-            for (uint32_t m = fmask; m;) {
-                const int L0 = __ffs(m) - 1;
-                m &= m - 1;
-                const int L1 = m ? __ffs(m) - 1 : -1;
-                if (m) m &= m - 1;
-                const int L = half ? L1 : L0;
-                const bool act = L >= 0;
-                const int Ls = act ? L : 0;
-                const int gs = Ls >= EVG_NUM_GROUPS ? 1 : 0;
-                const uint32_t gw0 = W.rec[2 * Ls], gw1 = W.rec[2 * Ls + 1];
-                const uint32_t gl = gw0 & W0_LOC_MASK;
-                const uint32_t galive = act ? gw1 & 0xFFFFu : 0u;
-                const int gsize = S.g_size[Ls];
-                const bool mine = (galive >> u) & 1u;
-                double* hp = A.health + env * S.health_slots + S.g_slot[Ls] + u;
+            // apply, server.py:573-643: four 8-slot segments per pass, one unit slot per lane.  Groups of
+            // more than 8 units span two segments; their healths go through shared memory so that the
+            // group lane can redo numpy's pairwise sum in order afterwards.
+            const int q8 = lane >> 3, u8 = lane & 7;
+            double* henv = A.health + env * S.health_slots;
+            for (int base = 0; base < nsegs; base += 4) {
+                const bool act = base + q8 < nsegs;
+                const uint32_t pr = act ? W.seg[base + q8] : 0u;
+                const int L = pr & 31, sg = pr >> 5, slot = sg * 8 + u8;
+                const int gs = L >= EVG_NUM_GROUPS ? 1 : 0;
+                const uint32_t galive = act ? W.rec[2 * L + 1] & 0xFFFFu : 0u;
+                const int gsize = S.g_size[L];
+                const bool mine = (galive >> slot) & 1u;
+                double* hp = henv + S.g_slot[L] + slot;
                 double h = 0.0;
                 uint32_t d = 0;
                 if (mine) {
-                    const uint32_t idx = (W.cmd[Ls] & 0xFFu) + __popc(galive & ((1u << u) - 1u));
+                    const uint32_t idx = (W.cmd[L] & 0xFFu) + __popc(galive & ((1u << slot) - 1u));
                     d = (W.hist[gs * S.hist_words + (idx >> 1)] >> ((idx & 1u) * 16)) & 0xFFFFu;
                     h = *hp;
                 }
                 bool dead = false;
                 if (d) {
                     // loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
+                    const uint32_t gl = W.rec[2 * L] & W0_LOC_MASK;
                     const uint32_t nwd = W.rec[kRecNode0 + gl - 1];
                     const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
                     const int bonus = (cb == gs ? 1 : 0) + ((S.node_flags[gl] >> 2) & 1);
                     const double node_def = __dmul_rn((double)bonus, S.node_def[gl]);
-                    const double loss = __ddiv_rn(__dmul_rn(10.0, (double)d), __dadd_rn(S.unit_armor[S.g_type[Ls]], node_def));
+                    const double loss = __ddiv_rn(__dmul_rn(10.0, (double)d), __dadd_rn(S.unit_armor[S.g_type[L]], node_def));
                     h = __dsub_rn(h, loss);  // server.py:609
                     if (h <= 0.0) {          // server.py:615-618
                         h = 0.0;
@@ -326,18 +325,44 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                     }
                     *hp = h;
                 }
-                const uint32_t deadmask = (__ballot_sync(FULL, dead) >> (16 * half)) & 0xFFFFu;
-                const double hsum = half_pairwise_sum(S, h, gsize);
-                if (act && u == 0) {
-                    W.res[Ls] = galive & ~deadmask;
-                    W.hs[Ls] = hsum;
+                const uint32_t deadbits = (__ballot_sync(FULL, dead) >> (8 * q8)) & 0xFFu;
+                if (act && u8 == 0 && deadbits) atomicAnd(&W.res[L], ~(deadbits << (8 * sg)));
+                // np.sum(unitHealth), server.py:481: n == 8 is the pure 8-leaf tree, done in registers
+                double v = __dadd_rn(h, __shfl_xor_sync(FULL, h, 1, 8));
+                v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2, 8));
+                v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 4, 8));
+                if (S.has_small_groups) {  // n < 8: plain left-to-right loop from 0.0
+                    double seq = 0.0;
+                    for (int i = 0; i < 7; ++i) {
+                        const double x = __shfl_sync(FULL, h, i, 8);
+                        if (i < gsize) seq = __dadd_rn(seq, x);
+                    }
+                    if (gsize < 8) v = seq;
+                }
+                if (act) {
+                    if (gsize > 8) W.hbig[S.g_big[L] * 16 + slot] = h;  // slots >= size hold 0.0
+                    else if (u8 == 0) W.hs[L] = v;
                 }
             }
             __syncwarp();
             if (fighting) {
                 const uint32_t nalive = W.res[lane];
+                double hsum;
+                const int gsize = S.g_size[lane];
+                if (gsize > 8) {  // 8 < n <= 16: numpy's blocked pairwise sum, restated sequentially
+                    const double* a = W.hbig + S.g_big[lane] * 16;
+                    double r[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r[k] = gsize == 16 ? __dadd_rn(a[k], a[8 + k]) : a[k];
+                    hsum = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                     __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                    if (gsize < 16)
+                        for (int i = 8; i < gsize; ++i) hsum = __dadd_rn(hsum, a[i]);
+                } else {
+                    hsum = W.hs[lane];
+                }
                 // player_state's int((health*1.)/units_alive), server.py:491 — one division for all groups
-                const int avg = nalive ? (int)__ddiv_rn(W.hs[lane], (double)__popc(nalive)) : 0;
+                const int avg = nalive ? (int)__ddiv_rn(hsum, (double)__popc(nalive)) : 0;
                 w1 = (w1 & 0xFFFF0000u) | nalive;  // alive == 0: destroyed, leaves the node list (:623-627)
                 w0 = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
             }
@@ -413,17 +438,18 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
 
     // ---- reward / done, env.py:37-60.  float32(float64(score)/MAX_SCORE) == float32 IEEE division for
     // every score < 2^24 (no double-rounding case exists; checked exhaustively in tests/test_tape.py).
-    if (lane < 2) {
+    {
         const int mine = lane ? s1 : s0, other = lane ? s0 : s1;
         float r;
         if (done) r = mine == other ? 0.f : (mine > other ? 1.f : (lane ? -1.f : 0.f));
         else r = __fdiv_rn((float)mine, S.max_score_f);
-        A.reward[env * 2 + lane] = r;
-        if (A.scores) A.scores[env * 2 + lane] = mine;
-    }
-    if (lane == 0) {
-        A.done[env] = done ? 1 : 0;
-        if (A.status) A.status[env] = (uint8_t)status;
+        const float r1 = __shfl_sync(FULL, r, 1);
+        if (lane == 0) {
+            reinterpret_cast<float2*>(A.reward)[env] = make_float2(r, r1);
+            A.done[env] = done ? 1 : 0;
+            if (A.status) A.status[env] = (uint8_t)status;
+            if (A.scores) reinterpret_cast<int2*>(A.scores)[env] = make_int2(s0, s1);
+        }
     }
 
     // ---- observations of the post-turn state
@@ -470,7 +496,7 @@ __device__ __forceinline__ const Tables& stage_tables(const Tables& T, unsigned 
 }
 
 template <int NODES>
-__global__ void __launch_bounds__(kThreads) evg_step_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
+__global__ void __launch_bounds__(kThreads, 4) evg_step_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables& S = stage_tables(T, smem);

@@ -27,7 +27,8 @@ def sass_lines(path, kernel):
         m = re.search(r'//## File "(.*?)", line (\d+)', ln)
         if m:
             f = m.group(1).rsplit("/", 1)[-1]
-            cur_line = int(m.group(2)) if f.endswith(".cu") else "%s:%s" % (f, m.group(2))
+            if f.endswith(".cu"):
+                cur_line = int(m.group(2))  # instructions inlined from toolkit headers keep the last .cu line
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m:
@@ -61,11 +62,22 @@ def main():
         total += inst
     tot_smp = sum(p[2] for p in per.values())
     print("total warp instructions: %d, samples: %d" % (total, tot_smp))
+    if len(sys.argv) > 5:
+        import json
+        phases(per, total, json.load(open(sys.argv[5])))
     print("%5s %12s %6s %6s %8s %6s  %s" % ("line", "warp_inst", "share", "thr/in", "samples", "smp%", "source"))
     for line, p in sorted(per.items(), key=lambda kv: -kv[1][0])[:70]:
         s = src[line - 1].strip()[:90] if src and isinstance(line, int) and line <= len(src) else ""
         print("%5s %12d %5.1f%% %6.1f %8d %5.1f%%  %s" % (line, p[0], 100.0 * p[0] / max(total, 1), p[1] / max(p[0], 1), p[2],
                                                           100.0 * p[2] / max(tot_smp, 1), s))
+
+
+def phases(per, total, bounds):
+    """bounds: [(name, first_line, last_line)] -> instruction share per phase."""
+    print("--- per phase")
+    for name, a, b in bounds:
+        v = sum(p[0] for ln, p in per.items() if isinstance(ln, int) and a <= ln <= b)
+        print("%-28s %12d %5.1f%%" % (name, v, 100.0 * v / max(total, 1)))
 
 
 if __name__ == "__main__":
