@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 AUTORESET_OFF, AUTORESET_TERMINAL, AUTORESET_NEXT = 0, 1, 2
 STATUS_IN_PROGRESS, STATUS_TIME_EXPIRED, STATUS_BASE_CAPTURE, STATUS_ANNIHILATION = 0, 1, 2, 3
-BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_COUNT = 0, 1, 2, 3
+BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_COUNT = 0, 1, 2, 3, 4
 
 _N1 = MAX_NODES + 1
 
@@ -89,6 +89,7 @@ class EvgLayout(C.Structure):
         ("records_bytes", C.c_int64),
         ("health_bytes", C.c_int64),
         ("stats_bytes", C.c_int64),
+        ("tables_bytes", C.c_int64),
     ]
 
 

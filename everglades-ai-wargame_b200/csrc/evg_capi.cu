@@ -4,8 +4,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "evg_internal.h"
 
@@ -45,6 +47,8 @@ struct EvgSim {
     int64_t launches;
     int64_t steps;
     EvgLayout layout;
+    bool use_tpm;     // thread-per-match step kernel (default) or the warp-per-match one (EVG_STEP_KERNEL=warp)
+    size_t tpm_smem;
 };
 
 namespace {
@@ -102,9 +106,9 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
         t.ut_control[k] = (uint8_t)c.unit_control[k];
         t.ut_cost[k] = (uint8_t)c.unit_cost[k];
     }
-    int max_units = 0, max_size = 0, small = 0, per_player_slots = 0, n_big = 0;
+    int max_units = 0, max_size = 0, small = 0, per_player_slots = 0, n_big = 0, max_dmg_sum = 0;
     for (int p = 0; p < EVG_NUM_PLAYERS; ++p) {
-        int slots = 0, units = 0;
+        int slots = 0, units = 0, dmg_sum = 0;
         for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
             const int L = p * EVG_NUM_GROUPS + g, size = c.group_size[p][g], type = c.group_type[p][g];
             if (size < 1 || size > EVG_MAX_GROUP_UNITS) return fail(EVG_E_CONFIG, "group %d of player %d has %d units; supported 1..%d", g, p, size, EVG_MAX_GROUP_UNITS);
@@ -119,6 +123,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
             t.g_slot[L] = (uint16_t)slots;  // per-player offset for now
             slots += round_up(size, 4);     // every group starts on a 32-byte sector
             units += size;
+            dmg_sum += size * c.unit_damage[type];
             if (size > max_size) max_size = size;
             if (size < 8) small = 1;
             t.init_w0[L] = (uint32_t)start[p] | 100u << evg::W0_AVG_SHIFT;  // health 100.0 each (definitions.py:62)
@@ -126,6 +131,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
         }
         if (slots > per_player_slots) per_player_slots = slots;
         if (units > max_units) max_units = units;
+        if (dmg_sum > max_dmg_sum) max_dmg_sum = dmg_sum;
     }
     for (int g = 0; g < EVG_NUM_GROUPS; ++g) t.g_slot[EVG_NUM_GROUPS + g] = (uint16_t)(t.g_slot[EVG_NUM_GROUPS + g] + per_player_slots);
     t.health_slots = 2 * per_player_slots;
@@ -154,6 +160,16 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.sm_misc = t.sm_obs + round_up(2 * t.obs_len * 4, 16);
     t.sm_warp_stride = t.sm_misc + 528 + n_big * 16 * 8;
     t.sm_tables_bytes = round_up((int)sizeof(evg::Tables), 16);
+    // thread-per-match kernel: per-thread row = record + scratch; u8 histograms when no target can collect > 255 damage
+    t.tpm_hist16 = max_dmg_sum > 255 ? 1 : 0;
+    t.tpm_hwords = (max_units * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
+    {
+        const int scr_combat = nn + 2 * t.tpm_hwords, scr_post = 2 * nn + 32;
+        int pitch = t.rec_words8 * 2 + (scr_combat > scr_post ? scr_combat : scr_post);
+        pitch += pitch & 1;
+        if (((pitch / 2) & 1) == 0) pitch += 2;  // pitch/2 odd: conflict-free 4- and 8-byte column accesses
+        t.tpm_pitch = pitch;
+    }
     *out = t;
     return EVG_OK;
 }
@@ -251,6 +267,9 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     s->launches = 0;
     s->steps = 0;
     s->smem = (size_t)t.sm_tables_bytes + 128 + (size_t)evg::kWarpsPerBlock * t.sm_warp_stride;
+    const char* which = getenv("EVG_STEP_KERNEL");
+    s->use_tpm = !(which && strcmp(which, "warp") == 0);
+    if ((e = evg::tpm_prepare(t, &s->tpm_smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(tpm smem)"); }
     if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
     int per_sm = 0;
     if ((e = evg::step_occupancy(t, s->smem, &per_sm)) != cudaSuccess || per_sm < 1) { delete s; return cuda_fail(e, "occupancy query"); }
@@ -267,6 +286,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.records_bytes = n_envs * L.record_bytes;
     L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
     L.stats_bytes = evg::ST_COUNT * 8;
+    L.tables_bytes = (int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * evg::kLossD * 8;
     *out = s;
     return EVG_OK;
 }
@@ -293,6 +313,27 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
         if (!device_ptrs[i]) return fail(EVG_E_ARG, "bind slot %d is null", i);
         if ((uintptr_t)device_ptrs[i] % 16) return fail(EVG_E_ARG, "bind slot %d is not 16-byte aligned", i);
         sim->bound[i] = device_ptrs[i];
+    }
+    // derived table: the fp64 quotient of server.py:601 for every (unit type, node, bonus, damage sum < 32),
+    // computed on the host in IEEE double (same operation order as the kernel's fallback division)
+    {
+        const EvgConfig& c = sim->cfg;
+        const int nn = c.n_nodes + 1;
+        std::vector<double> tab((size_t)c.n_unit_types * nn * 3 * evg::kLossD, 0.0);
+        for (int t = 0; t < c.n_unit_types; ++t)
+            for (int x = 1; x <= c.n_nodes; ++x)
+                for (int b = 0; b < 3; ++b) {
+                    volatile double node_def = (double)b * c.node_defense[x];
+                    volatile double divisor = c.unit_armor[t] + node_def;
+                    for (int d = 0; d < evg::kLossD; ++d) {
+                        volatile double num = 10.0 * (double)d;
+                        tab[((size_t)(t * nn + x) * 3 + b) * evg::kLossD + d] = num / divisor;
+                    }
+                }
+        cudaError_t e = cudaSetDevice(sim->device);
+        if (e == cudaSuccess) e = cudaMemcpy(device_ptrs[EVG_BIND_TABLES], tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "upload of the loss table");
+        sim->tables.loss_tab = (const double*)device_ptrs[EVG_BIND_TABLES];
     }
     sim->is_bound = true;
     return EVG_OK;
@@ -332,8 +373,9 @@ int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward
     a.status = d_status;
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
-    cudaError_t e = evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "evg_step_kernel launch");
+    cudaError_t e = sim->use_tpm ? evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, (cudaStream_t)stream)
+                                 : evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;
     sim->steps += 1;
     return EVG_OK;

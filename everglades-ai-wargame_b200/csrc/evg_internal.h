@@ -60,7 +60,13 @@ struct Tables {
     uint8_t g_big[kGroupLanes];  // ordinal among the groups with more than 8 units (index into the hbig scratch)
     uint8_t g_damage[kGroupLanes], g_speed[kGroupLanes], g_control[kGroupLanes], g_cost[kGroupLanes];  // per group lane
     uint8_t edge[kNN][kNN];
+    // thread-per-match kernel (evg_step_tpm.cu): per-thread shared-memory row geometry, in 32-bit words
+    int32_t tpm_pitch, tpm_hwords, tpm_hist16, tpm_pad;
+    const double* loss_tab;  // [type][node][bonus][32]: (10.*d)/(armor + bonus*StructureDefense), d < 32
 };
+
+constexpr int kLossD = 32;
+constexpr int kTpmThreads = 128;
 
 // device statistics accumulators (uint64 each); matches EvgEpisodeStats minus env_turns
 enum { ST_EPISODES = 0, ST_WIN0, ST_WIN1, ST_TIES, ST_TURNS, ST_SCORE0, ST_SCORE1, ST_STATUS0, ST_COUNT = ST_STATUS0 + 4 };
@@ -90,5 +96,24 @@ cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t
                                 cudaStream_t stream);
 cudaError_t step_occupancy(const Tables& t, size_t smem, int* blocks_per_sm);
 cudaError_t set_step_smem(size_t smem);
+// thread-per-match step (evg_step_tpm.cu)
+cudaError_t tpm_prepare(const Tables& t, size_t* smem_out);
+cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, cudaStream_t stream);
+
+#ifdef __CUDACC__
+// Philox4x32-10 (Salmon et al., SC'11); same function as oracle/tape.py, oracle/evg_oracle.c.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                               uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        if (r) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+#endif
 
 }  // namespace evg

@@ -51,20 +51,6 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, const Tables& S)
     return W;
 }
 
-// Philox4x32-10 (Salmon et al., SC'11); same function as oracle/tape.py, oracle/evg_oracle.c.
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                               uint32_t out[4])
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        if (r) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 // Compile-time map size (NODES > 0: DemoMap's 11 is the instantiated fast path) or run-time (0).
 template <int NODES>
 struct Dim {
@@ -245,25 +231,21 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                 W.cmd[lane] = tb | hb << 8 | n << 16;
                 W.res[lane] = alive;
             }
-            // work lists: (group, block of 4 attackers) for the draws, (group, 8-slot segment) for the apply
-            const uint32_t nblk = fighting ? (cnt + 3) >> 2 : 0;
-            const uint32_t b1 = fmask, b2 = __ballot_sync(FULL, nblk >= 2), b3 = __ballot_sync(FULL, nblk >= 3),
-                           b4 = __ballot_sync(FULL, nblk >= 4);
+            // work lists: (group, block of 8 attackers) for the draws, (group, 8-slot segment) for the apply
             const uint32_t big = __ballot_sync(FULL, fighting && S.g_size[lane] > 8);
+            const uint32_t b2 = __ballot_sync(FULL, fighting && cnt > 8);
             const uint32_t lt = (1u << lane) - 1u;
-            const int o1 = __popc(b1), o2 = o1 + __popc(b2), o3 = o2 + __popc(b3), npairs = o3 + __popc(b4);
-            const int nsegs = o1 + __popc(big);
-            if (nblk >= 1) {
-                W.pair[__popc(b1 & lt)] = (uint8_t)lane;
-                W.seg[__popc(b1 & lt)] = (uint8_t)lane;
+            const int o1 = __popc(fmask), npairs = o1 + __popc(b2), nsegs = o1 + __popc(big);
+            if (fighting) {
+                W.pair[__popc(fmask & lt)] = (uint8_t)lane;
+                W.seg[__popc(fmask & lt)] = (uint8_t)lane;
             }
-            if (nblk >= 2) W.pair[o1 + __popc(b2 & lt)] = (uint8_t)(lane | 1 << 5);
-            if (nblk >= 3) W.pair[o2 + __popc(b3 & lt)] = (uint8_t)(lane | 2 << 5);
-            if (nblk >= 4) W.pair[o3 + __popc(b4 & lt)] = (uint8_t)(lane | 3 << 5);
+            if ((b2 >> lane) & 1u) W.pair[o1 + __popc(b2 & lt)] = (uint8_t)(lane | 1 << 5);
             if ((big >> lane) & 1u) W.seg[o1 + __popc(big & lt)] = (uint8_t)(lane | 1 << 5);
             __syncwarp();
             // draws: every alive unit of a fighting group targets uid = randint(opposing alive units
-            // at the node) and adds its type's damage to infliction[uid], server.py:549-566
+            // at the node) and adds its type's damage to infliction[uid], server.py:549-566.
+            // Tape: 8 draws of 16 bits per Philox block (oracle/tape.py).
             for (int base = 0; base < npairs; base += 32) {
                 const int p = base + lane;
                 if (p < npairs) {
@@ -280,9 +262,10 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                                   episode << 8, S.seed_lo, S.seed_hi, r);
                     uint32_t* hist = W.hist + (1 - gs) * S.hist_words;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (4 * k + q < gcnt) {
-                            const uint32_t idx = ghb + __umulhi(r[q], gn);
+                    for (int q = 0; q < 8; ++q)
+                        if (8 * k + q < gcnt) {
+                            const uint32_t half = (q & 1) ? r[q >> 1] >> 16 : r[q >> 1] & 0xFFFFu;
+                            const uint32_t idx = ghb + ((half * gn) >> 16);
                             atomicAdd(&hist[idx >> 1], dmg << ((idx & 1u) * 16));
                         }
                 }

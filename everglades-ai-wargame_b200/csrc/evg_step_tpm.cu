@@ -1,0 +1,499 @@
+// evg_step_tpm.cu — the turn step with ONE THREAD PER MATCH (a CTA = a block slice of 128 matches).
+//
+// Why: ncu on the warp-per-match kernel (profiles/r1_*) showed it issue-bound at ~1000 warp
+// instructions per match-turn with only ~18 of 32 lanes active: the per-turn work of one match is too
+// small and too irregular to fill a warp.  Here every lane runs a whole match, so the regular phases
+// (actions, movement, capture, scoring, observation packing) execute with all 32 lanes busy and no
+// shuffles, ballots or atomics; only combat diverges (different matches fight different amounts).
+//
+// Memory behaviour stays that of the warp kernel — HBM sees the same bytes:
+//   * the 256-byte records of a warp's 32 matches are loaded/stored COOPERATIVELY (coalesced 16-byte
+//     accesses) into per-thread rows of shared memory; row pitch P has P/2 odd, so "every thread reads
+//     word w of its own row" is bank-conflict free for 4- and 8-byte accesses;
+//   * observations are packed by each thread into a 128-byte staging window of its row and streamed
+//     out by the warp as contiguous float2 runs (two matches per store instruction);
+//   * unit health is read as whole 64/96-byte group rows (full 32-byte sectors), only for groups that
+//     fight, and only hit units are written back.
+// Scratch per thread (dynamic indexing needs addressable storage): node member masks, two damage
+// histograms, capture accumulators.  IEEE fp64 health arithmetic as in the reference; the per-hit
+// division is a lookup in a host-built table of the SAME fp64 quotients for damage sums < 32.
+//
+// Reference semantics are cited per phase (server.py / env.py as in evg_kernels.cu); the checker is
+// oracle/evg_oracle.c.
+#include "evg_internal.h"
+
+namespace evg {
+
+namespace {
+
+template <int NODES>
+struct Geo {
+    const Tables& S;
+    __device__ __forceinline__ explicit Geo(const Tables& s) : S(s) {}
+    __device__ __forceinline__ int n_nodes() const { return NODES ? NODES : S.n_nodes; }
+    __device__ __forceinline__ int nn() const { return n_nodes() + 1; }
+    __device__ __forceinline__ int obs_len() const { return 1 + 4 * n_nodes() + 5 * EVG_NUM_GROUPS; }
+    __device__ __forceinline__ int rw() const { return NODES ? ((kRecNode0 + NODES) * 4 + 31) / 32 * 8 : S.rec_words8 * 2; }
+};
+
+// numpy's pairwise float64 sum (np.sum at server.py:481) over hv[0..size), size <= MAXSZ <= 16.
+template <int MAXSZ>
+__device__ __forceinline__ double np_sum_regs(const double (&hv)[MAXSZ], int size)
+{
+    if (MAXSZ < 8 || size < 8) {  // n < 8: left to right from 0.0
+        double res = 0.0;
+#pragma unroll
+        for (int i = 0; i < (MAXSZ < 7 ? MAXSZ : 7); ++i)
+            if (i < size) res = __dadd_rn(res, hv[i]);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r[k] = hv[k];
+        if (MAXSZ == 16 && size == 16) r[k] = __dadd_rn(hv[k], hv[8 + k]);  // one more block of 8
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int i = 8; i < (MAXSZ < 15 ? MAXSZ : 15); ++i)
+        if (i < size && size < 16) res = __dadd_rn(res, hv[i]);  // remainder, sequential
+    return res;
+}
+
+// One side's target group: read its health row, apply the damage histogram, write hit units back.
+// Returns the new alive mask and stores the observation's avg health (server.py:573-643, :480-491).
+template <int MAXSZ, typename HistT>
+__device__ __forceinline__ uint32_t apply_group(const Tables& S, double* hp, int size, uint32_t alive0, const HistT* hist, int tb,
+                                                const double* ltab, double divisor, int* avg_out)
+{
+    double hv[MAXSZ];
+#pragma unroll
+    for (int u = 0; u < MAXSZ; u += 2) {
+        if (u < size) {  // groups start on 32-byte sectors and are padded to 4 slots: pairs never leave the row
+            const double2 t = *reinterpret_cast<const double2*>(hp + u);
+            hv[u] = t.x;
+            hv[u + 1] = t.y;
+        } else {
+            hv[u] = 0.0;
+            hv[u + 1] = 0.0;
+        }
+    }
+    uint32_t alive = alive0;
+    int rank = 0;
+#pragma unroll
+    for (int u = 0; u < MAXSZ; ++u) {
+        if (u < size && ((alive0 >> u) & 1u)) {
+            const uint32_t d = hist[tb + rank];  // infliction[uid]: uid -> r-th unit alive before combat
+            ++rank;
+            if (d) {
+                // loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
+                const double loss = d < (uint32_t)kLossD ? ltab[d] : __ddiv_rn(__dmul_rn(10.0, (double)d), divisor);
+                double h = __dsub_rn(hv[u], loss);  // server.py:609
+                if (h <= 0.0) {                     // server.py:615-618
+                    h = 0.0;
+                    alive &= ~(1u << u);
+                }
+                hv[u] = h;
+                hp[u] = h;
+            }
+        }
+    }
+    const double hsum = np_sum_regs<MAXSZ>(hv, size);
+    *avg_out = alive ? (int)__ddiv_rn(hsum, (double)__popc(alive)) : 0;  // int((health*1.)/units_alive), :491
+    return alive;
+}
+
+template <int NODES, int MAXSZ, typename HistT, int PITCH>
+__global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    // ---- stage the static tables once per CTA
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&T);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    const Tables& S = *reinterpret_cast<const Tables*>(smem);
+    unsigned long long* cta_stats = reinterpret_cast<unsigned long long*>(smem + T.sm_tables_bytes);
+    if (threadIdx.x < ST_COUNT) cta_stats[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const Geo<NODES> G(S);
+    const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
+    const int P = PITCH ? PITCH : T.tpm_pitch;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes + 128);
+    uint32_t* wrow = rows + (size_t)warp * 32 * P;  // the warp's 32 rows
+    uint32_t* R = wrow + (size_t)lane * P;          // my record
+    uint32_t* X = R + RW;                           // my scratch
+    const int64_t warp_env0 = (int64_t)blockIdx.x * kTpmThreads + warp * 32;
+    const int64_t env = warp_env0 + lane;
+    const int64_t left = A.n_envs - warp_env0;
+    const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+    const bool valid = lane < nvalid;
+
+    // ---- cooperative, coalesced load of the warp's records into the per-thread rows
+    {
+        const int q4 = RW / 4;  // 16-byte chunks per record
+        const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + warp_env0 * q4;
+        const int total = nvalid * q4;
+        for (int f = lane; f < total; f += 32) {
+            const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
+            const uint4 v = g4[f];
+            uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
+            d[0] = make_uint2(v.x, v.y);
+            d[1] = make_uint2(v.z, v.w);
+        }
+    }
+    __syncwarp();
+
+    uint32_t turn = 0, episode = 0;
+    int s0 = 0, s1 = 0, status = 0;
+    bool done = false;
+    if (valid) {
+        turn = R[kRecTurn] + 1u;  // server.py:214
+        episode = R[kRecEpisode];
+
+        // ---- action decode + validation, server.py:218-271 (rows in order; first valid row per group wins)
+        {
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(A.actions) + env * 7;
+            uint32_t used = 0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const uint32_t w = aw[k];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int r = 2 * k + hlf;
+                    const uint32_t a = (w >> (16 * hlf)) & 0xFFFFu;
+                    const int ag = (int)(int8_t)(a & 0xFFu);
+                    int an = (int)(int8_t)(a >> 8);
+                    const int pl = r >= EVG_MAX_ACTIONS ? 1 : 0;
+                    if ((unsigned)ag < (unsigned)EVG_NUM_GROUPS) {
+                        an = (unsigned)an <= (unsigned)n_nodes ? an : 0;
+                        if (pl) an = S.p1_map[an];  // server.py:233-234
+                        const int L = pl * EVG_NUM_GROUPS + ag;
+                        const uint32_t gw0 = R[2 * L];
+                        const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
+                        if (d && !(gw0 & W0_MOVING) && !((used >> L) & 1u)) {  // t3, t2, t1 (:241-250)
+                            used |= 1u << L;
+                            R[2 * L] = (gw0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | (uint32_t)an << W0_DEST_SHIFT |
+                                       d << W0_DIST_SHIFT | W0_READY;  // :267-270
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- combat, server.py:503-654
+        {
+            // member masks of the groups present (listed, not in transit) at each node, :516-535
+            for (int i = 0; i < nn; ++i) X[i] = 0;
+#pragma unroll
+            for (int L = 0; L < kGroupLanes; ++L) {
+                const uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
+                if ((w1 & 0xFFFFu) && !(w0 & W0_MOVING)) X[w0 & W0_LOC_MASK] |= 1u << L;
+            }
+            uint32_t contested = 0;
+            for (int x = 1; x <= n_nodes; ++x) {
+                const uint32_t m = X[x];
+                if ((m & 0xFFFu) && (m >> EVG_NUM_GROUPS)) contested |= 1u << (x - 1);  // both players present, :539
+            }
+            HistT* hist = reinterpret_cast<HistT*>(X + nn);  // [2][hwords*4/sizeof(HistT)]: targets of side 0, side 1
+            const int hstride = S.tpm_hwords * 4 / (int)sizeof(HistT);
+            double* henv = A.health + env * S.health_slots;
+            for (uint32_t cm = contested; cm; cm &= cm - 1) {
+                const int x = __ffs(cm);  // node id
+                const uint32_t mem = X[x];
+                // alive units per side = np.sum(counts[pid]), :552-553
+                uint32_t tot[2] = {0u, 0u};
+                for (uint32_t m = mem; m; m &= m - 1) {
+                    const int L = __ffs(m) - 1;
+                    tot[L >= EVG_NUM_GROUPS ? 1 : 0] += __popc(R[2 * L + 1] & 0xFFFFu);
+                }
+                for (int i = 0; i < (int)((tot[0] * sizeof(HistT) + 3) / 4); ++i) reinterpret_cast<uint32_t*>(hist)[i] = 0;
+                for (int i = 0; i < (int)((tot[1] * sizeof(HistT) + 3) / 4); ++i) reinterpret_cast<uint32_t*>(hist + hstride)[i] = 0;
+                // draws, :549-566: unit j of group gid targets uid = tape(...) among the opposing units at the
+                // node; 8 draws of 16 bits per Philox block (oracle/tape.py)
+                for (uint32_t m = mem; m; m &= m - 1) {
+                    const int L = __ffs(m) - 1;
+                    const int gs = L >= EVG_NUM_GROUPS ? 1 : 0, gg = L - gs * EVG_NUM_GROUPS;
+                    const int cnt = __popc(R[2 * L + 1] & 0xFFFFu);
+                    const uint32_t n = tot[1 - gs], dmg = S.g_damage[L];
+                    HistT* h = hist + (1 - gs) * hstride;
+                    for (int b = 0; 8 * b < cnt; ++b) {
+                        uint32_t r[4];
+                        philox4x32_10(S.env_base + (uint32_t)env, turn, (uint32_t)x | (uint32_t)gs << 8 | (uint32_t)gg << 16 | (uint32_t)b << 24,
+                                      episode << 8, S.seed_lo, S.seed_hi, r);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (8 * b + q < cnt) {
+                                const uint32_t half = (q & 1) ? r[q >> 1] >> 16 : r[q >> 1] & 0xFFFFu;
+                                h[(half * n) >> 16] += (HistT)dmg;
+                            }
+                    }
+                }
+                // apply, :573-643: both sides drew on pre-combat counts (:572), so the order of the two
+                // sides does not matter; inside a side, groups take histogram ranges in node-list order
+                // (arrival turn, then gid: the order of node.groups[pid], :198,690-691)
+                const uint32_t nwd = R[kRecNode0 + x - 1];
+                const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
+                const int fort = (S.node_flags[x] >> 2) & 1;
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    uint32_t rem = side ? mem >> EVG_NUM_GROUPS : mem & 0xFFFu;
+                    const int bonus = (cb == side ? 1 : 0) + fort;
+                    int tb = 0;
+                    while (rem) {
+                        int best = 0;
+                        uint32_t bestkey = 0xFFFFFFFFu;
+                        for (uint32_t m = rem; m; m &= m - 1) {
+                            const int g = __ffs(m) - 1;
+                            const uint32_t key = (R[2 * (side * EVG_NUM_GROUPS + g) + 1] >> 16) << 4 | (uint32_t)g;
+                            if (key < bestkey) { bestkey = key; best = g; }
+                        }
+                        rem &= ~(1u << best);
+                        const int L = side * EVG_NUM_GROUPS + best;
+                        const uint32_t w1 = R[2 * L + 1];
+                        const uint32_t alive0 = w1 & 0xFFFFu;
+                        const int type = S.g_type[L];
+                        const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
+                        const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
+                        int avg;
+                        const uint32_t alive = apply_group<MAXSZ, HistT>(S, henv + S.g_slot[L], S.g_size[L], alive0, hist + side * hstride, tb,
+                                                                         ltab, divisor, &avg);
+                        tb += __popc(alive0);
+                        R[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
+                        R[2 * L] = (R[2 * L] & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
+                    }
+                }
+            }
+        }
+
+        // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
+        //   [0:10) units of all listed groups (:446-449), [10:24) count*control of non-moving groups (:718-724),
+        //   [24:29) number of non-moving groups (:725-726); plus unit points for the score (:313-317)
+        for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
+        bool any_alive = false;
+#pragma unroll
+        for (int L = 0; L < kGroupLanes; ++L) {
+            uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
+            const uint32_t alive = w1 & 0xFFFFu;
+            if (alive) {  // destroyed groups are skipped, :663
+                if (w0 & W0_READY) {
+                    w0 = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
+                } else if (w0 & W0_MOVING) {
+                    const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[L];  // :671
+                    if (dist <= 0) {  // arrived: appended to the destination's list (:678-695)
+                        w0 = (w0 & (127u << W0_AVG_SHIFT)) | ((w0 >> W0_DEST_SHIFT) & 0x3Fu);
+                        w1 = alive | turn << 16;
+                        R[2 * L + 1] = w1;
+                    } else {
+                        w0 = (w0 & ~(0xFFu << W0_DIST_SHIFT)) | (uint32_t)dist << W0_DIST_SHIFT;
+                    }
+                }
+                R[2 * L] = w0;
+                const uint32_t cnt = __popc(alive);
+                uint32_t v = cnt;
+                if (!(w0 & W0_MOVING)) v |= (cnt * S.g_control[L]) << 10 | 1u << 24;
+                X[(L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK)] += v;
+                const int pts = (int)cnt * (int)S.g_cost[L];
+                if (L >= EVG_NUM_GROUPS) s1 += pts; else s0 += pts;
+                any_alive = true;
+            }
+        }
+
+        // ---- capture (server.py:708-767; current_turn > 0 here) and node scoring (server.py:298-310)
+        bool basecap = false;
+        for (int n = 1; n <= n_nodes; ++n) {
+            uint32_t nw = R[kRecNode0 + n - 1];
+            int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
+            const uint32_t a0 = X[n], a1 = X[nn + n];
+            const bool c0 = (a0 >> 24) != 0, c1 = (a1 >> 24) != 0;
+            const int cp = S.node_cp[n];
+            if (c0 != c1) {  // exactly one controller (:729)
+                const int pid = c1 ? 1 : 0;
+                if (abs(cs) < cp || pid != cb) {  // :731-732
+                    const int pts = (int)(((pid ? a1 : a0) >> 10) & 0x3FFFu), pxer = pid ? -1 : 1;
+                    const bool old_sign = cs < 0;  // :747-750, zero counts as player 0's sign
+                    cs += pts * pxer;
+                    const bool neutralize = old_sign != (cs < 0);
+                    if (abs(cs) >= cp) {  // :763-765
+                        cs = cp * pxer;
+                        cb = pid;
+                    }
+                    if (cb != -1 && neutralize) cb = -1;  // :766-767
+                    nw = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
+                    R[kRecNode0 + n - 1] = nw;
+                }
+            }
+            const int ts = S.node_team_start[n];
+            if (ts != -1 && cb != -1 && cb != ts) {
+                basecap = true;
+                if (cb) s1 += S.capture_bonus; else s0 += S.capture_bonus;
+            }
+            if (cs != 0) {
+                const int pts = abs(cs) == cp ? 2 * cp : abs(cs);
+                if (cs > 0) s0 += pts; else s1 += pts;
+            }
+        }
+        if ((int)turn >= S.turn_limit) status = EVG_STATUS_TIME_EXPIRED;  // server.py:321-328, in that priority
+        else if (!any_alive) status = EVG_STATUS_ANNIHILATION;
+        else if (basecap) status = EVG_STATUS_BASE_CAPTURE;
+        done = status != 0;
+
+        // ---- reward / done, env.py:37-60 (float32 division == float32(float64 quotient), tests/test_tape.py)
+        float r0, r1;
+        if (done) {
+            r0 = s0 > s1 ? 1.f : 0.f;
+            r1 = s1 > s0 ? 1.f : (s1 < s0 ? -1.f : 0.f);
+        } else {
+            r0 = __fdiv_rn((float)s0, S.max_score_f);
+            r1 = __fdiv_rn((float)s1, S.max_score_f);
+        }
+        reinterpret_cast<float2*>(A.reward)[env] = make_float2(r0, r1);
+        A.done[env] = done ? 1 : 0;
+        if (A.status) A.status[env] = (uint8_t)status;
+        if (A.scores) reinterpret_cast<int2*>(A.scores)[env] = make_int2(s0, s1);
+
+        // ---- episode end: statistics; EVG_AUTORESET_NEXT shows the NEW match's first observation
+        if (done && S.auto_reset != EVG_AUTORESET_OFF) {
+            atomicAdd(&cta_stats[ST_EPISODES], 1ull);
+            atomicAdd(&cta_stats[s0 == s1 ? ST_TIES : (s0 > s1 ? ST_WIN0 : ST_WIN1)], 1ull);
+            atomicAdd(&cta_stats[ST_TURNS], (unsigned long long)turn);
+            atomicAdd(&cta_stats[ST_SCORE0], (unsigned long long)s0);
+            atomicAdd(&cta_stats[ST_SCORE1], (unsigned long long)s1);
+            atomicAdd(&cta_stats[ST_STATUS0 + status], 1ull);
+        }
+    }
+    const bool reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
+    auto reset_row = [&]() {  // game_init state, server.py:133-209
+        for (int L = 0; L < kGroupLanes; ++L) {
+            R[2 * L] = S.init_w0[L];
+            R[2 * L + 1] = S.init_w1[L];
+        }
+        for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
+        turn = 0;
+        episode += 1;
+        double2* hp = reinterpret_cast<double2*>(A.health + env * S.health_slots);
+        for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
+    };
+    if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
+        reset_row();
+        for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
+        for (int L = 0; L < kGroupLanes; ++L) {
+            const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
+            X[(L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK)] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;
+        }
+    }
+
+    // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
+    // Each thread packs 32 floats at a time into the staging window of its row; the warp streams the
+    // windows out as contiguous float2 runs (2 matches x 128 B per store instruction).
+    {
+        float2* stage = reinterpret_cast<float2*>(X + 2 * nn);  // rows, RW and 2*nn are even: 8-byte aligned
+        const int stage_off = RW + 2 * nn;
+        const int npairs = OL;  // 2*OL floats per match = OL float2
+        float* obs_base = A.obs + warp_env0 * 2 * OL;
+        auto value = [&](int f) -> float {  // f = index into the match's 2*OL floats
+            const int p = f >= OL ? 1 : 0, i = f - p * OL;
+            if (i == 0) return (float)turn;
+            if (i < 1 + 4 * n_nodes) {
+                const int k = (i - 1) >> 2, j = (i - 1) & 3;
+                const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
+                if (j == 0) return (float)(S.node_flags[x] & 1u);
+                if (j == 1) return (float)((S.node_flags[x] >> 1) & 1u);
+                if (j == 2) return (float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu);  // raw sign for both viewers
+                return (float)(X[(p ? 0 : nn) + x] & 1023u);                                  // opposing listed units
+            }
+            const int q = i - 1 - 4 * n_nodes, g = q / 5, j = q - 5 * g;
+            const int L = p * EVG_NUM_GROUPS + g;
+            const uint32_t w0 = R[2 * L];
+            if (j == 0) return (float)(p ? (uint32_t)S.p1_map[w0 & W0_LOC_MASK] : (w0 & W0_LOC_MASK));
+            if (j == 1) return (float)S.g_type[L];
+            if (j == 2) return (float)((w0 >> W0_AVG_SHIFT) & 127u);
+            if (j == 3) return (float)((w0 >> 21) & 1u);
+            return (float)__popc(R[2 * L + 1] & 0xFFFFu);
+        };
+        const int half = lane >> 4, c16 = lane & 15;
+        const int nchunks = (npairs + 15) / 16;
+#pragma unroll
+        for (int c = 0; c < (NODES ? (1 + 4 * NODES + 60 + 15) / 16 : nchunks); ++c) {
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int pr = 16 * c + k;
+                    if (pr < npairs) stage[k] = make_float2(value(2 * pr), value(2 * pr + 1));
+                }
+            }
+            __syncwarp();
+            const int pr = 16 * c + c16;
+            if (pr < npairs) {
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                    const int m = 2 * it + half;
+                    if (m < nvalid) {
+                        const float2 v = *reinterpret_cast<const float2*>(wrow + (size_t)m * P + stage_off + 2 * c16);
+                        __stcs(reinterpret_cast<float2*>(obs_base + (size_t)m * 2 * OL) + pr, v);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (reset_now && S.auto_reset == EVG_AUTORESET_TERMINAL) reset_row();
+    if (valid) {
+        R[kRecTurn] = turn;
+        R[kRecEpisode] = episode;
+    }
+    __syncwarp();
+
+    // ---- cooperative, coalesced store of the records
+    {
+        const int q4 = RW / 4;
+        uint4* g4 = reinterpret_cast<uint4*>(A.records) + warp_env0 * q4;
+        const int total = nvalid * q4;
+        for (int f = lane; f < total; f += 32) {
+            const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
+            const uint2* s = reinterpret_cast<const uint2*>(wrow + (size_t)m * P + 4 * q);
+            const uint2 a = s[0], b = s[1];
+            g4[f] = make_uint4(a.x, a.y, b.x, b.y);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ST_COUNT && cta_stats[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], cta_stats[threadIdx.x]);
+}
+
+// which instantiation serves this config
+enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
+
+Variant pick(const Tables& t)
+{
+    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == 126) return V_FAST;
+    return t.tpm_hist16 ? V_GENERIC16 : V_GENERIC8;
+}
+
+}  // namespace
+
+cudaError_t tpm_prepare(const Tables& t, size_t* smem_out)
+{
+    const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kTpmThreads * t.tpm_pitch * 4;
+    *smem_out = smem;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, 126>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned)((a.n_envs + kTpmThreads - 1) / kTpmThreads);
+    switch (pick(t)) {
+        case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, 126><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        default: evg_step_tpm_kernel<0, 16, uint16_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace evg

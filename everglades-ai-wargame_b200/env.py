@@ -69,13 +69,15 @@ class BatchedEvergladesEnv:
             self._records = torch.empty(lay.records_bytes, dtype=torch.uint8, device=self.device)
             self._health = torch.empty(lay.health_bytes // 8, dtype=torch.float64, device=self.device)
             self._stats = torch.zeros(lay.stats_bytes // 8, dtype=torch.int64, device=self.device)
+            self._tables = torch.zeros(lay.tables_bytes // 8, dtype=torch.float64, device=self.device)
             self.obs = torch.empty((N, 2, self.obs_len), dtype=torch.float32, device=self.device)
             self.reward = torch.empty((N, 2), dtype=torch.float32, device=self.device)
             self.done = torch.empty((N,), dtype=torch.uint8, device=self.device)
             self.status = torch.empty((N,), dtype=torch.uint8, device=self.device)
             self.scores = torch.empty((N, 2), dtype=torch.int32, device=self.device)
             self._actions = torch.zeros((N, 2, _capi.MAX_ACTIONS, 2), dtype=torch.int8, device=self.device)
-        ptrs = (C.c_void_p * _capi.BIND_COUNT)(self._records.data_ptr(), self._health.data_ptr(), self._stats.data_ptr())
+        ptrs = (C.c_void_p * _capi.BIND_COUNT)(self._records.data_ptr(), self._health.data_ptr(), self._stats.data_ptr(),
+                                               self._tables.data_ptr())
         _capi.check(self._lib.evg_bind(self._h, ptrs, _capi.BIND_COUNT))
         self._host = None
         self._is_reset = False

@@ -133,12 +133,14 @@ typedef struct EvgLayout {
     int64_t records_bytes; /* = n_envs * record_bytes           (bind slot EVG_BIND_RECORDS) */
     int64_t health_bytes;  /* = n_envs * health_slots * 8       (bind slot EVG_BIND_HEALTH)  */
     int64_t stats_bytes;   /* episode statistics accumulators   (bind slot EVG_BIND_STATS)   */
+    int64_t tables_bytes;  /* derived lookup tables, filled by evg_bind (bind slot EVG_BIND_TABLES) */
 } EvgLayout;
 
 #define EVG_BIND_RECORDS 0
 #define EVG_BIND_HEALTH 1
 #define EVG_BIND_STATS 2
-#define EVG_BIND_COUNT 3
+#define EVG_BIND_TABLES 3
+#define EVG_BIND_COUNT 4
 
 /* Episode statistics accumulated on the device by evg_step (matches that ended). */
 typedef struct EvgEpisodeStats {
@@ -166,7 +168,8 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
 int evg_destroy(EvgSim* sim);
 
 int evg_layout(const EvgSim* sim, EvgLayout* out);
-/* Bind caller-owned device arrays (index = EVG_BIND_*). Must precede reset/step. */
+/* Bind caller-owned device arrays (index = EVG_BIND_*). Must precede reset/step.  Uploads the derived
+ * tables into slot EVG_BIND_TABLES (synchronous copy). */
 int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs);
 
 /* Put matches into the post-game_init state (server.py:133-209, env.py:75-116) and write their

@@ -65,9 +65,12 @@ static uint32_t tape_word(uint64_t seed, uint64_t env, uint32_t episode, uint32_
 static uint32_t combat_draw(uint64_t seed, uint64_t env, uint32_t episode, int turn, int node, int side, int gid, int j,
                             uint32_t n)
 {
+    /* 8 draws of 16 bits per Philox block: word (j>>1)&3, low half for even j, high half for odd j */
     uint32_t c2 = (uint32_t)(node & 0xFF) | (uint32_t)(side & 0xFF) << 8 | (uint32_t)(gid & 0xFF) << 16 |
-                  (uint32_t)((j >> 2) & 0xFF) << 24;
-    return (uint32_t)(((uint64_t)tape_word(seed, env, episode, (uint32_t)turn, c2, 0u, j) * n) >> 32);
+                  (uint32_t)((j >> 3) & 0xFF) << 24;
+    uint32_t w = tape_word(seed, env, episode, (uint32_t)turn, c2, 0u, j >> 1);
+    uint32_t r = (j & 1) ? w >> 16 : w & 0xFFFFu;
+    return (r * n) >> 16;
 }
 
 /* ------------------------------------------------------------------ numpy float64 sum */

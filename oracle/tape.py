@@ -9,10 +9,11 @@ pure function that returns the value of every combat draw from its position
 in the game.  The position visible at the reference call site (frame locals of
 ``EvergladesGame.combat``) is (turn, node.ID, pid, gid, j); the tape is
 
-    r   = philox4x32_10(key=(seed_lo, seed_hi),
-                        ctr=(env, turn, node | pid<<8 | gid<<16 | (j>>2)<<24,
-                             DOMAIN | episode<<8))[j & 3]
-    uid = (r * n) >> 32                      # n = opposing alive units at the node
+    w   = philox4x32_10(key=(seed_lo, seed_hi),
+                        ctr=(env, turn, node | pid<<8 | gid<<16 | (j>>3)<<24,
+                             DOMAIN | episode<<8))[(j >> 1) & 3]
+    r   = (w >> 16) if (j & 1) else (w & 0xFFFF)        # 8 draws of 16 bits per Philox block
+    uid = (r * n) >> 16                      # n = opposing alive units at the node (< 2^16)
 
 Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
 (SC'11); constants below are the published ones and `philox4x32` is checked
@@ -45,13 +46,14 @@ def philox4x32(ctr, key, rounds: int = 10):
 
 
 def combat_word(seed: int, env: int, turn: int, node: int, side: int, gid: int, j: int, episode: int = 0) -> int:
-    """The raw 32-bit tape word for the j-th alive attacker of (side, gid) at `node`."""
-    ctr = (env & MASK, turn & MASK, (node & 0xFF) | (side & 0xFF) << 8 | (gid & 0xFF) << 16 | ((j >> 2) & 0xFF) << 24,
+    """The raw 16-bit tape value for the j-th alive attacker of (side, gid) at `node`."""
+    ctr = (env & MASK, turn & MASK, (node & 0xFF) | (side & 0xFF) << 8 | (gid & 0xFF) << 16 | ((j >> 3) & 0xFF) << 24,
            DOMAIN_COMBAT | (episode & 0xFFFFFF) << 8)
     key = (seed & MASK, (seed >> 32) & MASK)
-    return philox4x32(ctr, key)[j & 3]
+    w = philox4x32(ctr, key)[(j >> 1) & 3]
+    return (w >> 16) if (j & 1) else (w & 0xFFFF)
 
 
 def combat_draw(seed: int, env: int, turn: int, node: int, side: int, gid: int, j: int, n: int, episode: int = 0) -> int:
     """Value the patched ``np.random.randint(n)`` returns at server.py:562."""
-    return (combat_word(seed, env, turn, node, side, gid, j, episode) * int(n)) >> 32
+    return (combat_word(seed, env, turn, node, side, gid, j, episode) * int(n)) >> 16

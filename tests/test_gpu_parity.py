@@ -250,3 +250,10 @@ def test_step_host_equals_step(evg, eo, cfg):
         assert np.array_equal(rew.numpy(), orew.astype(np.float32))
         assert np.array_equal(done.numpy(), odone)
     assert env.h2d_bytes_per_step() == n * 28 and env.d2h_bytes_per_step() == n * (840 + 8 + 1)
+
+
+def test_warp_per_match_kernel_still_matches_oracle(evg, eo, cfg, monkeypatch):
+    """The earlier warp-per-match step kernel stays selectable (EVG_STEP_KERNEL=warp) for A/B profiling."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", "warp")
+    rng = np.random.default_rng(31)
+    run_against_oracle(evg, eo, cfg, 1024, 150, seed=19, first=7, make_actions=lambda s: adjacent_actions(rng, s, cfg))
