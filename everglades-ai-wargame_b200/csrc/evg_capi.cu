@@ -164,7 +164,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.tpm_hist16 = max_dmg_sum > 255 ? 1 : 0;
     t.tpm_hwords = (max_units * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
     {
-        const int scr_combat = nn + 2 * t.tpm_hwords, scr_post = 2 * nn + 32;
+        const int scr_combat = 2 * nn + 2 * t.tpm_hwords, scr_post = 2 * nn + 32;
         int pitch = t.rec_words8 * 2 + (scr_combat > scr_post ? scr_combat : scr_post);
         pitch += pitch & 1;
         if (((pitch / 2) & 1) == 0) pitch += 2;  // pitch/2 odd: conflict-free 4- and 8-byte column accesses

@@ -4,7 +4,11 @@
 // instructions per match-turn with only ~18 of 32 lanes active: the per-turn work of one match is too
 // small and too irregular to fill a warp.  Here every lane runs a whole match, so the regular phases
 // (actions, movement, capture, scoring, observation packing) execute with all 32 lanes busy and no
-// shuffles, ballots or atomics; only combat diverges (different matches fight different amounts).
+// shuffles, ballots or atomics.  Combat is the irregular part (matches fight different amounts), so it
+// is WARP-COOPERATIVE: the fighting groups of the warp's 32 matches form one work list and every
+// lane takes one (match, group) item at a time — draws into that match's shared-memory histogram
+// with atomics, then the whole group's fp64 health update — so lanes stay busy however unevenly the
+// fights are spread over the matches.
 //
 // Memory behaviour stays that of the warp kernel — HBM sees the same bytes:
 //   * the 256-byte records of a warp's 32 matches are loaded/stored COOPERATIVELY (coalesced 16-byte
@@ -104,6 +108,35 @@ __device__ __forceinline__ uint32_t apply_group(const Tables& S, double* hp, int
     return alive;
 }
 
+// game_init state (server.py:133-209) for one match: record row in shared memory + health refill
+__device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* health, int n_nodes)
+{
+    for (int L = 0; L < kGroupLanes; ++L) {
+        R[2 * L] = S.init_w0[L];
+        R[2 * L + 1] = S.init_w1[L];
+    }
+    for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
+    double2* hp = reinterpret_cast<double2*>(health);
+    for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
+}
+
+// k-th (0-based) set bit of a 24-bit mask
+__device__ __forceinline__ int kth_set_bit(uint32_t mask, int k)
+{
+    int pos = 0;
+    int t = __popc(mask & 0xFFFu);
+    if (k >= t) { pos = 12; k -= t; mask >>= 12; }
+    t = __popc(mask & 0x3Fu);
+    if (k >= t) { pos += 6; k -= t; mask >>= 6; }
+    t = __popc(mask & 0x7u);
+    if (k >= t) { pos += 3; k -= t; mask >>= 3; }
+    t = mask & 1u;
+    if (k >= t) { pos += 1; k -= t; mask >>= 1; }
+    t = mask & 1u;
+    if (k >= t) pos += 1;
+    return pos;
+}
+
 template <int NODES, int MAXSZ, typename HistT, int PITCH>
 __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
@@ -138,6 +171,7 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         const int q4 = RW / 4;  // 16-byte chunks per record
         const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + warp_env0 * q4;
         const int total = nvalid * q4;
+#pragma unroll 4
         for (int f = lane; f < total; f += 32) {
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
             const uint4 v = g4[f];
@@ -185,97 +219,141 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             }
         }
 
-        // ---- combat, server.py:503-654
-        {
-            // member masks of the groups present (listed, not in transit) at each node, :516-535
+        // (combat runs warp-cooperatively below, outside this per-thread block)
+    }
+
+    // ---- combat, server.py:503-654
+    {
+        // per-thread preparation, scratch layout (words): X[0..nn) member masks of the groups present at
+        // each node, X[nn..2nn) per-node totals and histogram bases, X[2nn..) two damage histograms
+        uint32_t fm = 0;  // my match's fighting groups
+        if (valid) {
             for (int i = 0; i < nn; ++i) X[i] = 0;
-#pragma unroll
-            for (int L = 0; L < kGroupLanes; ++L) {
+#pragma unroll 4
+            for (int L = 0; L < kGroupLanes; ++L) {  // listed and not in transit, :516-535
                 const uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
                 if ((w1 & 0xFFFFu) && !(w0 & W0_MOVING)) X[w0 & W0_LOC_MASK] |= 1u << L;
             }
-            uint32_t contested = 0;
+            uint32_t b0 = 0, b1 = 0;
             for (int x = 1; x <= n_nodes; ++x) {
-                const uint32_t m = X[x];
-                if ((m & 0xFFFu) && (m >> EVG_NUM_GROUPS)) contested |= 1u << (x - 1);  // both players present, :539
-            }
-            HistT* hist = reinterpret_cast<HistT*>(X + nn);  // [2][hwords*4/sizeof(HistT)]: targets of side 0, side 1
-            const int hstride = S.tpm_hwords * 4 / (int)sizeof(HistT);
-            double* henv = A.health + env * S.health_slots;
-            for (uint32_t cm = contested; cm; cm &= cm - 1) {
-                const int x = __ffs(cm);  // node id
                 const uint32_t mem = X[x];
-                // alive units per side = np.sum(counts[pid]), :552-553
-                uint32_t tot[2] = {0u, 0u};
-                for (uint32_t m = mem; m; m &= m - 1) {
-                    const int L = __ffs(m) - 1;
-                    tot[L >= EVG_NUM_GROUPS ? 1 : 0] += __popc(R[2 * L + 1] & 0xFFFFu);
-                }
-                for (int i = 0; i < (int)((tot[0] * sizeof(HistT) + 3) / 4); ++i) reinterpret_cast<uint32_t*>(hist)[i] = 0;
-                for (int i = 0; i < (int)((tot[1] * sizeof(HistT) + 3) / 4); ++i) reinterpret_cast<uint32_t*>(hist + hstride)[i] = 0;
-                // draws, :549-566: unit j of group gid targets uid = tape(...) among the opposing units at the
-                // node; 8 draws of 16 bits per Philox block (oracle/tape.py)
-                for (uint32_t m = mem; m; m &= m - 1) {
-                    const int L = __ffs(m) - 1;
-                    const int gs = L >= EVG_NUM_GROUPS ? 1 : 0, gg = L - gs * EVG_NUM_GROUPS;
-                    const int cnt = __popc(R[2 * L + 1] & 0xFFFFu);
-                    const uint32_t n = tot[1 - gs], dmg = S.g_damage[L];
-                    HistT* h = hist + (1 - gs) * hstride;
-                    for (int b = 0; 8 * b < cnt; ++b) {
-                        uint32_t r[4];
-                        philox4x32_10(S.env_base + (uint32_t)env, turn, (uint32_t)x | (uint32_t)gs << 8 | (uint32_t)gg << 16 | (uint32_t)b << 24,
-                                      episode << 8, S.seed_lo, S.seed_hi, r);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (8 * b + q < cnt) {
-                                const uint32_t half = (q & 1) ? r[q >> 1] >> 16 : r[q >> 1] & 0xFFFFu;
-                                h[(half * n) >> 16] += (HistT)dmg;
-                            }
+                if ((mem & 0xFFFu) && (mem >> EVG_NUM_GROUPS)) {  // both players present: contested, :539
+                    fm |= mem;
+                    uint32_t t0 = 0, t1 = 0;  // np.sum(counts[pid]), :552-553
+                    for (uint32_t m = mem; m; m &= m - 1) {
+                        const int L = __ffs(m) - 1;
+                        const uint32_t c = __popc(R[2 * L + 1] & 0xFFFFu);
+                        if (L >= EVG_NUM_GROUPS) t1 += c; else t0 += c;
                     }
-                }
-                // apply, :573-643: both sides drew on pre-combat counts (:572), so the order of the two
-                // sides does not matter; inside a side, groups take histogram ranges in node-list order
-                // (arrival turn, then gid: the order of node.groups[pid], :198,690-691)
-                const uint32_t nwd = R[kRecNode0 + x - 1];
-                const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
-                const int fort = (S.node_flags[x] >> 2) & 1;
-#pragma unroll
-                for (int side = 0; side < 2; ++side) {
-                    uint32_t rem = side ? mem >> EVG_NUM_GROUPS : mem & 0xFFFu;
-                    const int bonus = (cb == side ? 1 : 0) + fort;
-                    int tb = 0;
-                    while (rem) {
-                        int best = 0;
-                        uint32_t bestkey = 0xFFFFFFFFu;
-                        for (uint32_t m = rem; m; m &= m - 1) {
-                            const int g = __ffs(m) - 1;
-                            const uint32_t key = (R[2 * (side * EVG_NUM_GROUPS + g) + 1] >> 16) << 4 | (uint32_t)g;
-                            if (key < bestkey) { bestkey = key; best = g; }
-                        }
-                        rem &= ~(1u << best);
-                        const int L = side * EVG_NUM_GROUPS + best;
-                        const uint32_t w1 = R[2 * L + 1];
-                        const uint32_t alive0 = w1 & 0xFFFFu;
-                        const int type = S.g_type[L];
-                        const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
-                        const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
-                        int avg;
-                        const uint32_t alive = apply_group<MAXSZ, HistT>(S, henv + S.g_slot[L], S.g_size[L], alive0, hist + side * hstride, tb,
-                                                                         ltab, divisor, &avg);
-                        tb += __popc(alive0);
-                        R[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
-                        R[2 * L] = (R[2 * L] & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
-                    }
+                    X[nn + x] = t0 | t1 << 8 | b0 << 16 | b1 << 24;  // node-local uid -> histogram slot base
+                    b0 += t0;
+                    b1 += t1;
                 }
             }
+            uint32_t* H = X + 2 * nn;
+            for (int i = 0; i < (int)((b0 * sizeof(HistT) + 3) / 4); ++i) H[i] = 0;
+            for (int i = 0; i < (int)((b1 * sizeof(HistT) + 3) / 4); ++i) H[S.tpm_hwords + i] = 0;
         }
+        __syncwarp();  // rows (actions applied, masks, zeroed histograms) are read by other lanes from here on
+        // the warp's work list = concatenation of the matches' fighting groups; a round takes whole
+        // matches (a match has <= 24 items), so draws and apply of one match stay in one round
+        const int nitems = __popc(fm);
+        int incl = nitems;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int pre = incl - nitems;
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        int m_begin = 0;
+        while (total && m_begin < 32) {
+            const int base = __shfl_sync(0xFFFFFFFFu, pre, m_begin);
+            const int m_end = __popc(__ballot_sync(0xFFFFFFFFu, incl - base <= 32));
+            const int nround = __shfl_sync(0xFFFFFFFFu, incl, m_end - 1) - base;
+            const int q = base + lane;
+            int m = 0;  // largest m with pre[m] <= q
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const int cand = m + step;
+                const int pc = __shfl_sync(0xFFFFFFFFu, pre, cand & 31);
+                if (cand < 32 && pc <= q) m = cand;
+            }
+            const int pm = __shfl_sync(0xFFFFFFFFu, pre, m);
+            const uint32_t fmm = __shfl_sync(0xFFFFFFFFu, fm, m);
+            const bool act = lane < nround;
+            // item state kept across the two phases
+            uint32_t* Rm = wrow + (size_t)m * P;
+            uint32_t* Xm = Rm + RW;
+            int L = 0, side = 0, x = 1, tb = 0;
+            uint32_t w0 = 0, w1 = 0;
+            if (act) {
+                L = kth_set_bit(fmm, q - pm);
+                side = L >= EVG_NUM_GROUPS ? 1 : 0;
+                const int gg = L - side * EVG_NUM_GROUPS;
+                w0 = Rm[2 * L];
+                w1 = Rm[2 * L + 1];
+                x = (int)(w0 & W0_LOC_MASK);
+                const int cnt = __popc(w1 & 0xFFFFu);
+                const uint32_t info = Xm[nn + x];
+                const uint32_t n = side ? info & 0xFFu : (info >> 8) & 0xFFu;       // opposing units at the node
+                const uint32_t hb = side ? (info >> 16) & 0xFFu : info >> 24;       // opposing histogram base
+                tb = (int)(side ? info >> 24 : (info >> 16) & 0xFFu);               // my side's base at this node
+                // my group's range starts after the groups listed before it (arrival order, then gid:
+                // node.groups[pid], :198,690-691); sibling counts are still pre-combat here
+                const uint32_t key = (w1 >> 16) << 4 | (uint32_t)gg;
+                for (uint32_t sm = (side ? Xm[x] >> EVG_NUM_GROUPS : Xm[x] & 0xFFFu) & ~(1u << gg); sm; sm &= sm - 1) {
+                    const int g = __ffs(sm) - 1;
+                    const uint32_t w1g = Rm[2 * (side * EVG_NUM_GROUPS + g) + 1];
+                    if (((w1g >> 16) << 4 | (uint32_t)g) < key) tb += __popc(w1g & 0xFFFFu);
+                }
+                // draws, :549-566: unit j targets uid = tape(...) among the opposing units at the node and adds
+                // its type's damage to infliction[uid]; 8 draws of 16 bits per Philox block (oracle/tape.py)
+                const uint32_t dmg = S.g_damage[L];
+                const uint32_t turn_m = Rm[kRecTurn] + 1u, ep_m = Rm[kRecEpisode];
+                uint32_t* hw = Xm + 2 * nn + (1 - side) * S.tpm_hwords;
+                for (int b = 0; 8 * b < cnt; ++b) {
+                    uint32_t r[4];
+                    philox4x32_10(S.env_base + (uint32_t)(warp_env0 + m), turn_m,
+                                  (uint32_t)x | (uint32_t)side << 8 | (uint32_t)gg << 16 | (uint32_t)b << 24, ep_m << 8, S.seed_lo, S.seed_hi, r);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (8 * b + k < cnt) {
+                            const uint32_t half = (k & 1) ? r[k >> 1] >> 16 : r[k >> 1] & 0xFFFFu;
+                            const uint32_t idx = hb + ((half * n) >> 16);
+                            if (sizeof(HistT) == 1) atomicAdd(&hw[idx >> 2], dmg << ((idx & 3u) * 8));
+                            else atomicAdd(&hw[idx >> 1], dmg << ((idx & 1u) * 16));
+                        }
+                }
+            }
+            __syncwarp();
+            // apply, :573-643: both sides drew on pre-combat counts (:572); one lane updates one whole group
+            if (act) {
+                const uint32_t nwd = Rm[kRecNode0 + x - 1];
+                const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
+                const int bonus = (cb == side ? 1 : 0) + ((S.node_flags[x] >> 2) & 1);
+                const int type = S.g_type[L];
+                const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
+                const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
+                const HistT* hist = reinterpret_cast<const HistT*>(Xm + 2 * nn + side * S.tpm_hwords);
+                double* hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
+                int avg;
+                const uint32_t alive = apply_group<MAXSZ, HistT>(S, hp, S.g_size[L], w1 & 0xFFFFu, hist, tb, ltab, divisor, &avg);
+                Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
+                Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
+            }
+            __syncwarp();
+            m_begin = m_end;
+        }
+    }
 
+    if (valid) {
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
         //   [0:10) units of all listed groups (:446-449), [10:24) count*control of non-moving groups (:718-724),
         //   [24:29) number of non-moving groups (:725-726); plus unit points for the score (:313-317)
         for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
         bool any_alive = false;
-#pragma unroll
+#pragma unroll 4
         for (int L = 0; L < kGroupLanes; ++L) {
             uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
             const uint32_t alive = w1 & 0xFFFFu;
@@ -367,19 +445,10 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         }
     }
     const bool reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
-    auto reset_row = [&]() {  // game_init state, server.py:133-209
-        for (int L = 0; L < kGroupLanes; ++L) {
-            R[2 * L] = S.init_w0[L];
-            R[2 * L + 1] = S.init_w1[L];
-        }
-        for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
+    if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
+        reset_row(S, R, A.health + env * S.health_slots, n_nodes);
         turn = 0;
         episode += 1;
-        double2* hp = reinterpret_cast<double2*>(A.health + env * S.health_slots);
-        for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
-    };
-    if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
-        reset_row();
         for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
         for (int L = 0; L < kGroupLanes; ++L) {
             const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
@@ -441,7 +510,11 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             __syncwarp();
         }
     }
-    if (reset_now && S.auto_reset == EVG_AUTORESET_TERMINAL) reset_row();
+    if (reset_now && S.auto_reset == EVG_AUTORESET_TERMINAL) {
+        reset_row(S, R, A.health + env * S.health_slots, n_nodes);
+        turn = 0;
+        episode += 1;
+    }
     if (valid) {
         R[kRecTurn] = turn;
         R[kRecEpisode] = episode;
@@ -453,6 +526,7 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         const int q4 = RW / 4;
         uint4* g4 = reinterpret_cast<uint4*>(A.records) + warp_env0 * q4;
         const int total = nvalid * q4;
+#pragma unroll 4
         for (int f = lane; f < total; f += 32) {
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
             const uint2* s = reinterpret_cast<const uint2*>(wrow + (size_t)m * P + 4 * q);
@@ -469,7 +543,7 @@ enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
 
 Variant pick(const Tables& t)
 {
-    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == 126) return V_FAST;
+    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == 138) return V_FAST;
     return t.tpm_hist16 ? V_GENERIC16 : V_GENERIC8;
 }
 
@@ -480,7 +554,7 @@ cudaError_t tpm_prepare(const Tables& t, size_t* smem_out)
     const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kTpmThreads * t.tpm_pitch * 4;
     *smem_out = smem;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, 126>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, 138>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
@@ -489,7 +563,7 @@ cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, cud
 {
     const unsigned grid = (unsigned)((a.n_envs + kTpmThreads - 1) / kTpmThreads);
     switch (pick(t)) {
-        case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, 126><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, 138><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
         case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
         default: evg_step_tpm_kernel<0, 16, uint16_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
     }
