@@ -65,24 +65,27 @@ __device__ __forceinline__ double np_sum_regs(const double (&hv)[MAXSZ], int siz
     return res;
 }
 
-// One side's target group: read its health row, apply the damage histogram, write hit units back.
-// Returns the new alive mask and stores the observation's avg health (server.py:573-643, :480-491).
-template <int MAXSZ, typename HistT>
-__device__ __forceinline__ uint32_t apply_group(const Tables& S, double* hp, int size, uint32_t alive0, const HistT* hist, int tb,
-                                                const double* ltab, double divisor, int* avg_out)
+// Read a group's health row (issued early so that DRAM latency overlaps the draws).  Groups start on
+// 32-byte sectors and are padded to 4 slots, so 16-byte pairs never leave the row.
+template <int MAXSZ>
+__device__ __forceinline__ void load_group(const double* __restrict__ hp, int size, double (&hv)[MAXSZ])
 {
-    double hv[MAXSZ];
 #pragma unroll
     for (int u = 0; u < MAXSZ; u += 2) {
-        if (u < size) {  // groups start on 32-byte sectors and are padded to 4 slots: pairs never leave the row
-            const double2 t = *reinterpret_cast<const double2*>(hp + u);
-            hv[u] = t.x;
-            hv[u + 1] = t.y;
-        } else {
-            hv[u] = 0.0;
-            hv[u + 1] = 0.0;
-        }
+        double2 t = make_double2(0.0, 0.0);
+        if (u < size) t = *reinterpret_cast<const double2*>(hp + u);
+        hv[u] = t.x;
+        hv[u + 1] = t.y;
     }
+}
+
+// One target group: apply the damage histogram to its units, write hit units back.  Returns the new
+// alive mask and the observation's avg health (server.py:573-643, :480-491).
+template <int MAXSZ, typename HistT>
+__device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
+                                                const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
+                                                int* avg_out)
+{
     uint32_t alive = alive0;
     int rank = 0;
 #pragma unroll
@@ -92,7 +95,7 @@ __device__ __forceinline__ uint32_t apply_group(const Tables& S, double* hp, int
             ++rank;
             if (d) {
                 // loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
-                const double loss = d < (uint32_t)kLossD ? ltab[d] : __ddiv_rn(__dmul_rn(10.0, (double)d), divisor);
+                const double loss = d < (uint32_t)kLossD ? __ldg(ltab + d) : __ddiv_rn(__dmul_rn(10.0, (double)d), divisor);
                 double h = __dsub_rn(hv[u], loss);  // server.py:609
                 if (h <= 0.0) {                     // server.py:615-618
                     h = 0.0;
@@ -148,8 +151,6 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     }
     const Tables& S = *reinterpret_cast<const Tables*>(smem);
-    unsigned long long* cta_stats = reinterpret_cast<unsigned long long*>(smem + T.sm_tables_bytes);
-    if (threadIdx.x < ST_COUNT) cta_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
     const Geo<NODES> G(S);
@@ -165,6 +166,11 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
     const int64_t left = A.n_envs - warp_env0;
     const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
     const bool valid = lane < nvalid;
+
+    // this turn's action rows (7 words per match), requested before the records so the latencies overlap
+    uint32_t aw[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) aw[k] = valid ? reinterpret_cast<const uint32_t*>(A.actions)[env * 7 + k] : 0u;
 
     // ---- cooperative, coalesced load of the warp's records into the per-thread rows
     {
@@ -191,7 +197,6 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 
         // ---- action decode + validation, server.py:218-271 (rows in order; first valid row per group wins)
         {
-            const uint32_t* aw = reinterpret_cast<const uint32_t*>(A.actions) + env * 7;
             uint32_t used = 0;
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
@@ -287,8 +292,12 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             uint32_t* Xm = Rm + RW;
             int L = 0, side = 0, x = 1, tb = 0;
             uint32_t w0 = 0, w1 = 0;
+            double hv[MAXSZ];
+            double* hp = A.health;
             if (act) {
                 L = kth_set_bit(fmm, q - pm);
+                hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
+                load_group<MAXSZ>(hp, S.g_size[L], hv);  // consumed after the draws
                 side = L >= EVG_NUM_GROUPS ? 1 : 0;
                 const int gg = L - side * EVG_NUM_GROUPS;
                 w0 = Rm[2 * L];
@@ -336,9 +345,8 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                 const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
                 const HistT* hist = reinterpret_cast<const HistT*>(Xm + 2 * nn + side * S.tpm_hwords);
-                double* hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
                 int avg;
-                const uint32_t alive = apply_group<MAXSZ, HistT>(S, hp, S.g_size[L], w1 & 0xFFFFu, hist, tb, ltab, divisor, &avg);
+                const uint32_t alive = apply_group<MAXSZ, HistT>(hp, hv, S.g_size[L], w1 & 0xFFFFu, hist, tb, ltab, divisor, &avg);
                 Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
                 Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
             }
@@ -353,31 +361,45 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         //   [24:29) number of non-moving groups (:725-726); plus unit points for the score (:313-317)
         for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
         bool any_alive = false;
-#pragma unroll 4
-        for (int L = 0; L < kGroupLanes; ++L) {
-            uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
-            const uint32_t alive = w1 & 0xFFFFu;
-            if (alive) {  // destroyed groups are skipped, :663
-                if (w0 & W0_READY) {
-                    w0 = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
-                } else if (w0 & W0_MOVING) {
-                    const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[L];  // :671
-                    if (dist <= 0) {  // arrived: appended to the destination's list (:678-695)
-                        w0 = (w0 & (127u << W0_AVG_SHIFT)) | ((w0 >> W0_DEST_SHIFT) & 0x3Fu);
-                        w1 = alive | turn << 16;
-                        R[2 * L + 1] = w1;
-                    } else {
-                        w0 = (w0 & ~(0xFFu << W0_DIST_SHIFT)) | (uint32_t)dist << W0_DIST_SHIFT;
+        {
+            uint32_t* __restrict__ acc0 = X;
+            uint32_t* __restrict__ acc1 = X + nn;
+            auto move = [&](int L, uint32_t& v, uint32_t& loc, int& pts) {
+                uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
+                const uint32_t alive = w1 & 0xFFFFu;
+                v = 0; loc = 0; pts = 0;
+                if (alive) {  // destroyed groups are skipped, :663
+                    if (w0 & W0_READY) {
+                        w0 = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
+                    } else if (w0 & W0_MOVING) {
+                        const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[L];  // :671
+                        if (dist <= 0) {  // arrived: appended to the destination's list (:678-695)
+                            w0 = (w0 & (127u << W0_AVG_SHIFT)) | ((w0 >> W0_DEST_SHIFT) & 0x3Fu);
+                            R[2 * L + 1] = alive | turn << 16;
+                        } else {
+                            w0 = (w0 & ~(0xFFu << W0_DIST_SHIFT)) | (uint32_t)dist << W0_DIST_SHIFT;
+                        }
                     }
+                    R[2 * L] = w0;
+                    const uint32_t cnt = __popc(alive);
+                    v = cnt;
+                    if (!(w0 & W0_MOVING)) v |= (cnt * S.g_control[L]) << 10 | 1u << 24;
+                    loc = w0 & W0_LOC_MASK;
+                    pts = (int)cnt * (int)S.g_cost[L];
+                    any_alive = true;
                 }
-                R[2 * L] = w0;
-                const uint32_t cnt = __popc(alive);
-                uint32_t v = cnt;
-                if (!(w0 & W0_MOVING)) v |= (cnt * S.g_control[L]) << 10 | 1u << 24;
-                X[(L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK)] += v;
-                const int pts = (int)cnt * (int)S.g_cost[L];
-                if (L >= EVG_NUM_GROUPS) s1 += pts; else s0 += pts;
-                any_alive = true;
+            };
+#pragma unroll 2
+            for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
+                uint32_t va, la, vb, lb;
+                int pa, pb;
+                move(g, va, la, pa);
+                move(EVG_NUM_GROUPS + g, vb, lb, pb);
+                const uint32_t a = acc0[la], b = acc1[lb];  // entry 0 collects the (zero) contributions of dead groups
+                acc0[la] = a + va;
+                acc1[lb] = b + vb;
+                s0 += pa;
+                s1 += pb;
             }
         }
 
@@ -434,17 +456,19 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         if (A.status) A.status[env] = (uint8_t)status;
         if (A.scores) reinterpret_cast<int2*>(A.scores)[env] = make_int2(s0, s1);
 
-        // ---- episode end: statistics; EVG_AUTORESET_NEXT shows the NEW match's first observation
-        if (done && S.auto_reset != EVG_AUTORESET_OFF) {
-            atomicAdd(&cta_stats[ST_EPISODES], 1ull);
-            atomicAdd(&cta_stats[s0 == s1 ? ST_TIES : (s0 > s1 ? ST_WIN0 : ST_WIN1)], 1ull);
-            atomicAdd(&cta_stats[ST_TURNS], (unsigned long long)turn);
-            atomicAdd(&cta_stats[ST_SCORE0], (unsigned long long)s0);
-            atomicAdd(&cta_stats[ST_SCORE1], (unsigned long long)s1);
-            atomicAdd(&cta_stats[ST_STATUS0 + status], 1ull);
-        }
     }
     const bool reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
+    // ---- episode end: statistics, aggregated over the warp before touching the global counters
+    if (__any_sync(0xFFFFFFFFu, reset_now)) {
+        const unsigned e = reset_now ? 1u : 0u;
+        const unsigned v[ST_COUNT] = {e, e && s0 > s1, e && s1 > s0, e && s0 == s1, e ? turn : 0u, e ? (unsigned)s0 : 0u,
+                                      e ? (unsigned)s1 : 0u, e && status == 0, e && status == 1, e && status == 2, e && status == 3};
+#pragma unroll
+        for (int k = 0; k < ST_COUNT; ++k) {
+            const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+            if (lane == 0 && sum) atomicAdd(&A.stats[k], (unsigned long long)sum);
+        }
+    }
     if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
         reset_row(S, R, A.health + env * S.health_slots, n_nodes);
         turn = 0;
@@ -534,8 +558,6 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             g4[f] = make_uint4(a.x, a.y, b.x, b.y);
         }
     }
-    __syncthreads();
-    if (threadIdx.x < ST_COUNT && cta_stats[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], cta_stats[threadIdx.x]);
 }
 
 // which instantiation serves this config
