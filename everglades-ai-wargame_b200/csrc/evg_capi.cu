@@ -49,6 +49,7 @@ struct EvgSim {
     EvgLayout layout;
     bool use_tpm;     // thread-per-match step kernel (default) or the warp-per-match one (EVG_STEP_KERNEL=warp)
     size_t tpm_smem;
+    int tpm_grid;  // persistent CTAs: SMs x resident CTAs
 };
 
 namespace {
@@ -269,7 +270,9 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     s->smem = (size_t)t.sm_tables_bytes + 128 + (size_t)evg::kWarpsPerBlock * t.sm_warp_stride;
     const char* which = getenv("EVG_STEP_KERNEL");
     s->use_tpm = !(which && strcmp(which, "warp") == 0);
-    if ((e = evg::tpm_prepare(t, &s->tpm_smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(tpm smem)"); }
+    int tpm_per_sm = 0;
+    if ((e = evg::tpm_prepare(t, &s->tpm_smem, &tpm_per_sm)) != cudaSuccess || tpm_per_sm < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
+    s->tpm_grid = prop.multiProcessorCount * tpm_per_sm;
     if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
     int per_sm = 0;
     if ((e = evg::step_occupancy(t, s->smem, &per_sm)) != cudaSuccess || per_sm < 1) { delete s; return cuda_fail(e, "occupancy query"); }
@@ -373,7 +376,7 @@ int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward
     a.status = d_status;
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
-    cudaError_t e = sim->use_tpm ? evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, (cudaStream_t)stream)
+    cudaError_t e = sim->use_tpm ? evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream)
                                  : evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;

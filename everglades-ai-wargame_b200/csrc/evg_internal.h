@@ -97,8 +97,8 @@ cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t
 cudaError_t step_occupancy(const Tables& t, size_t smem, int* blocks_per_sm);
 cudaError_t set_step_smem(size_t smem);
 // thread-per-match step (evg_step_tpm.cu)
-cudaError_t tpm_prepare(const Tables& t, size_t* smem_out);
-cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, cudaStream_t stream);
+cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm);
+cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // Philox4x32-10 (Salmon et al., SC'11); same function as oracle/tape.py, oracle/evg_oracle.c.

@@ -73,7 +73,7 @@ __device__ __forceinline__ void load_group(const double* __restrict__ hp, int si
 #pragma unroll
     for (int u = 0; u < MAXSZ; u += 2) {
         double2 t = make_double2(0.0, 0.0);
-        if (u < size) t = *reinterpret_cast<const double2*>(hp + u);
+        if (u < size) t = __ldcs(reinterpret_cast<const double2*>(hp + u));
         hv[u] = t.x;
         hv[u + 1] = t.y;
     }
@@ -86,24 +86,38 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
                                                 const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
                                                 int* avg_out)
 {
-    uint32_t alive = alive0;
+    // pass 1: damage aimed at every alive unit.  infliction[uid]: uid -> r-th unit alive before combat
+    uint32_t dv[MAXSZ];
     int rank = 0;
+    uint32_t dmax = 0;
 #pragma unroll
     for (int u = 0; u < MAXSZ; ++u) {
-        if (u < size && ((alive0 >> u) & 1u)) {
-            const uint32_t d = hist[tb + rank];  // infliction[uid]: uid -> r-th unit alive before combat
-            ++rank;
-            if (d) {
-                // loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
-                const double loss = d < (uint32_t)kLossD ? __ldg(ltab + d) : __ddiv_rn(__dmul_rn(10.0, (double)d), divisor);
-                double h = __dsub_rn(hv[u], loss);  // server.py:609
-                if (h <= 0.0) {                     // server.py:615-618
-                    h = 0.0;
-                    alive &= ~(1u << u);
-                }
-                hv[u] = h;
-                hp[u] = h;
+        const bool on = u < size && ((alive0 >> u) & 1u);
+        dv[u] = on ? (uint32_t)hist[tb + rank] : 0u;
+        rank += on ? 1 : 0;
+        dmax = max(dmax, dv[u]);
+    }
+    // pass 2: loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601, from the
+    // table of those same fp64 quotients; all lookups are independent and issued together (ltab[0] == 0.0)
+    double loss[MAXSZ];
+#pragma unroll
+    for (int u = 0; u < MAXSZ; ++u) loss[u] = __ldg(ltab + min(dv[u], (uint32_t)(kLossD - 1)));
+    if (dmax >= (uint32_t)kLossD) {  // damage sums beyond the table: the division itself
+#pragma unroll
+        for (int u = 0; u < MAXSZ; ++u)
+            if (dv[u] >= (uint32_t)kLossD) loss[u] = __ddiv_rn(__dmul_rn(10.0, (double)dv[u]), divisor);
+    }
+    uint32_t alive = alive0;
+#pragma unroll
+    for (int u = 0; u < MAXSZ; ++u) {
+        if (dv[u]) {
+            double h = __dsub_rn(hv[u], loss[u]);  // server.py:609
+            if (h <= 0.0) {                        // server.py:615-618
+                h = 0.0;
+                alive &= ~(1u << u);
             }
+            hv[u] = h;
+            hp[u] = h;
         }
     }
     const double hsum = np_sum_regs<MAXSZ>(hv, size);
@@ -161,16 +175,29 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
     uint32_t* wrow = rows + (size_t)warp * 32 * P;  // the warp's 32 rows
     uint32_t* R = wrow + (size_t)lane * P;          // my record
     uint32_t* X = R + RW;                           // my scratch
-    const int64_t warp_env0 = (int64_t)blockIdx.x * kTpmThreads + warp * 32;
+    // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
+    // touches its own 32 rows, so batches need no CTA-wide barrier
+    const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
+    for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+    const int64_t warp_env0 = batch * kTpmThreads + warp * 32;
     const int64_t env = warp_env0 + lane;
     const int64_t left = A.n_envs - warp_env0;
     const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
     const bool valid = lane < nvalid;
+    {   // pull the NEXT batch's records and action rows towards L2 while this one is processed
+        const int64_t nenv0 = warp_env0 + (int64_t)gridDim.x * kTpmThreads;
+        if (nenv0 + 32 <= A.n_envs) {
+            const char* nr = reinterpret_cast<const char*>(A.records) + nenv0 * RW * 4;
+            for (int b = lane * 128; b < 32 * RW * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + b));
+            const char* na = reinterpret_cast<const char*>(A.actions) + nenv0 * 28;
+            if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(na + lane * 128));
+        }
+    }
 
     // this turn's action rows (7 words per match), requested before the records so the latencies overlap
     uint32_t aw[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) aw[k] = valid ? reinterpret_cast<const uint32_t*>(A.actions)[env * 7 + k] : 0u;
+    for (int k = 0; k < 7; ++k) aw[k] = valid ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
 
     // ---- cooperative, coalesced load of the warp's records into the per-thread rows
     {
@@ -180,7 +207,7 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 #pragma unroll 4
         for (int f = lane; f < total; f += 32) {
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
-            const uint4 v = g4[f];
+            const uint4 v = __ldcs(g4 + f);
             uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
             d[0] = make_uint2(v.x, v.y);
             d[1] = make_uint2(v.z, v.w);
@@ -253,6 +280,16 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                     X[nn + x] = t0 | t1 << 8 | b0 << 16 | b1 << 24;  // node-local uid -> histogram slot base
                     b0 += t0;
                     b1 += t1;
+                }
+            }
+            // the health rows of the groups that will fight: start them towards L2 now
+            {
+                const char* he = reinterpret_cast<const char*>(A.health + env * S.health_slots);
+                for (uint32_t m = fm; m; m &= m - 1) {
+                    const int L = __ffs(m) - 1;
+                    const char* hr = he + (size_t)S.g_slot[L] * 8;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(hr));
+                    if (S.g_size[L] > 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + 64));
                 }
             }
             uint32_t* H = X + 2 * nn;
@@ -558,6 +595,8 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             g4[f] = make_uint4(a.x, a.y, b.x, b.y);
         }
     }
+    __syncwarp();
+    }  // batch loop
 }
 
 // which instantiation serves this config
@@ -571,19 +610,28 @@ Variant pick(const Tables& t)
 
 }  // namespace
 
-cudaError_t tpm_prepare(const Tables& t, size_t* smem_out)
+cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
 {
     const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kTpmThreads * t.tpm_pitch * 4;
     *smem_out = smem;
     cudaError_t e;
+
     if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, 138>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    switch (pick(t)) {
+        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, 138>, kTpmThreads, smem); break;
+        case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint8_t, 0>, kTpmThreads, smem); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint16_t, 0>, kTpmThreads, smem); break;
+    }
+    if (e != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
-cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, cudaStream_t stream)
+cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream)
 {
-    const unsigned grid = (unsigned)((a.n_envs + kTpmThreads - 1) / kTpmThreads);
+    const int64_t nb = (a.n_envs + kTpmThreads - 1) / kTpmThreads;
+    const unsigned grid = (unsigned)(nb < max_grid ? nb : max_grid);
     switch (pick(t)) {
         case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, 138><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
         case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
