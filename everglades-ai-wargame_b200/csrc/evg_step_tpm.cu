@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
         const int q4 = RW / 4;  // 16-byte chunks per record
         const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + warp_env0 * q4;
         const int total = nvalid * q4;
-#pragma unroll 4
+#pragma unroll 8
         for (int f = lane; f < total; f += 32) {
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
             const uint4 v = __ldcs(g4 + f);
@@ -224,29 +224,34 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 
         // ---- action decode + validation, server.py:218-271 (rows in order; first valid row per group wins)
         {
+            // all 14 rows are decoded and looked up first (independent shared-memory reads in flight together:
+            // accepting a row changes neither the group's location nor its moving flag), then resolved in order
+            int Lr[2 * EVG_MAX_ACTIONS];
+            uint32_t dr[2 * EVG_MAX_ACTIONS], nr[2 * EVG_MAX_ACTIONS];
+#pragma unroll
+            for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) {
+                const uint32_t a = (aw[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+                const int ag = (int)(int8_t)(a & 0xFFu);
+                int an = (int)(int8_t)(a >> 8);
+                const int pl = r >= EVG_MAX_ACTIONS ? 1 : 0;
+                const bool okg = (unsigned)ag < (unsigned)EVG_NUM_GROUPS;
+                an = (unsigned)an <= (unsigned)n_nodes ? an : 0;
+                if (pl) an = S.p1_map[an];  // server.py:233-234
+                const int L = pl * EVG_NUM_GROUPS + (okg ? ag : 0);
+                const uint32_t gw0 = R[2 * L];
+                const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
+                Lr[r] = L;
+                nr[r] = (uint32_t)an;
+                dr[r] = (okg && !(gw0 & W0_MOVING)) ? d : 0u;  // t2 (not moving) and t3 (adjacent), :243-250
+            }
             uint32_t used = 0;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const uint32_t w = aw[k];
-#pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    const int r = 2 * k + hlf;
-                    const uint32_t a = (w >> (16 * hlf)) & 0xFFFFu;
-                    const int ag = (int)(int8_t)(a & 0xFFu);
-                    int an = (int)(int8_t)(a >> 8);
-                    const int pl = r >= EVG_MAX_ACTIONS ? 1 : 0;
-                    if ((unsigned)ag < (unsigned)EVG_NUM_GROUPS) {
-                        an = (unsigned)an <= (unsigned)n_nodes ? an : 0;
-                        if (pl) an = S.p1_map[an];  // server.py:233-234
-                        const int L = pl * EVG_NUM_GROUPS + ag;
-                        const uint32_t gw0 = R[2 * L];
-                        const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
-                        if (d && !(gw0 & W0_MOVING) && !((used >> L) & 1u)) {  // t3, t2, t1 (:241-250)
-                            used |= 1u << L;
-                            R[2 * L] = (gw0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | (uint32_t)an << W0_DEST_SHIFT |
-                                       d << W0_DIST_SHIFT | W0_READY;  // :267-270
-                        }
-                    }
+            for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) {
+                if (dr[r] && !((used >> Lr[r]) & 1u)) {  // t1: the group has no accepted command yet, :241
+                    used |= 1u << Lr[r];
+                    const uint32_t gw0 = R[2 * Lr[r]];
+                    R[2 * Lr[r]] = (gw0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | nr[r] << W0_DEST_SHIFT |
+                                   dr[r] << W0_DIST_SHIFT | W0_READY;  // :267-270
                 }
             }
         }
@@ -263,8 +268,8 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             for (int i = 0; i < nn; ++i) X[i] = 0;
 #pragma unroll 4
             for (int L = 0; L < kGroupLanes; ++L) {  // listed and not in transit, :516-535
-                const uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
-                if ((w1 & 0xFFFFu) && !(w0 & W0_MOVING)) X[w0 & W0_LOC_MASK] |= 1u << L;
+                const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);
+                if ((w.y & 0xFFFFu) && !(w.x & W0_MOVING)) X[w.x & W0_LOC_MASK] |= 1u << L;
             }
             uint32_t b0 = 0, b1 = 0;
             for (int x = 1; x <= n_nodes; ++x) {
@@ -402,8 +407,9 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             uint32_t* __restrict__ acc0 = X;
             uint32_t* __restrict__ acc1 = X + nn;
             auto move = [&](int L, uint32_t& v, uint32_t& loc, int& pts) {
-                uint32_t w0 = R[2 * L], w1 = R[2 * L + 1];
-                const uint32_t alive = w1 & 0xFFFFu;
+                const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);
+                uint32_t w0 = w.x;
+                const uint32_t alive = w.y & 0xFFFFu;
                 v = 0; loc = 0; pts = 0;
                 if (alive) {  // destroyed groups are skipped, :663
                     if (w0 & W0_READY) {
@@ -550,11 +556,12 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 #pragma unroll
         for (int c = 0; c < (NODES ? (1 + 4 * NODES + 60 + 15) / 16 : nchunks); ++c) {
             if (valid) {
+                float vals[32];  // all reads first (they can be merged and overlapped), then the staging stores
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int pr = 16 * c + k;
-                    if (pr < npairs) stage[k] = make_float2(value(2 * pr), value(2 * pr + 1));
-                }
+                for (int k = 0; k < 32; ++k) vals[k] = 32 * c + k < 2 * npairs ? value(32 * c + k) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (16 * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
             }
             __syncwarp();
             const int pr = 16 * c + c16;
