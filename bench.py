@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-One "step" = one game turn for every match of the batch (the random_actions agent kernel for both
-players + the fused turn-step kernel).  Workload (config.workload): BASELINE.json configs[4] at
+One "step" = one game turn for every match of the batch: the random_actions agent kernel for both
+players + the turn-step kernel (--agents fused: one launch of evg_step_agents does both).  Workload (config.workload): BASELINE.json configs[4] at
 N = 1 — DemoMap, both players random_actions, 1,048,576 lock-step matches per GPU with in-place
 auto-reset; matches shard across ranks with NO collective on the step path (weak scaling; the
 only exchange is an end-of-run all_gather of episode statistics).
@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--agents", default="kernel", choices=["kernel", "fused"],
+                    help="random_actions rows from the agent kernel (2 launches/step) or generated inside the step kernel (1 launch)")
     return ap.parse_args()
 
 
@@ -59,7 +61,7 @@ def workload_config(args, world):
         "workload": "DemoMap random_actions self-match, %d lock-step matches per GPU, auto-reset "
                     "(BASELINE.json configs[4] at N=1; weak-scaled over ranks)" % args.envs_per_gpu,
         "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
-        "map": "DemoMap.json", "agents": "random_actions vs random_actions (on-device, Philox tape)",
+        "map": "DemoMap.json", "agents": "random_actions vs random_actions (on-device, Philox tape; %s)" % args.agents,
         "turn_limit": 150, "auto_reset": "terminal-obs", "seed": args.seed,
         "l2": "resident state %.2f GB/GPU >> 126 MB L2; no flush between steps" % (args.envs_per_gpu * (256 + 1600) / 1e9),
         "parallelism": "match-sharded x%d, no step-path collective" % world,
@@ -226,9 +228,13 @@ def main():
     env.reset()
     stream = torch.cuda.current_stream(dev)
 
+    fused = args.agents == "fused"
+
     def one_step():
-        a = env.random_actions()  # kernel 1: both players' random_actions rows
-        env.step(a)               # kernel 2: the fused turn step
+        if fused:
+            env.step_agents()                   # ONE launch: both players' random_actions rows + the whole turn
+        else:
+            env.step(env.random_actions())      # agent kernel, then the turn-step kernel
 
     for _ in range(args.warmup):
         one_step()
@@ -246,9 +252,12 @@ def main():
     clocks.start()
     t_begin.record(stream)
     for k in range(K):
-        a = env.random_actions()
+        a = None if fused else env.random_actions()
         ev[k][0].record(stream)
-        env.step(a)
+        if fused:
+            env.step_agents()
+        else:
+            env.step(a)
         ev[k][1].record(stream)
     t_end.record(stream)
     torch.cuda.synchronize(dev)

@@ -20,6 +20,7 @@ ABI_VERSION = 1
 
 AUTORESET_OFF, AUTORESET_TERMINAL, AUTORESET_NEXT = 0, 1, 2
 STATUS_IN_PROGRESS, STATUS_TIME_EXPIRED, STATUS_BASE_CAPTURE, STATUS_ANNIHILATION = 0, 1, 2, 3
+AGENT_EXTERNAL, AGENT_RANDOM = 0, 1
 BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_COUNT = 0, 1, 2, 3, 4
 
 _N1 = MAX_NODES + 1
@@ -144,6 +145,7 @@ SYMBOLS = [
     ("evg_bind", C.c_int, [_P, C.POINTER(_P), C.c_int32]),
     ("evg_reset", C.c_int, [_P, _P, _P, _P]),
     ("evg_step", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    ("evg_step_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_step_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_export_state", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     ("evg_import_state", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),

@@ -359,13 +359,13 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream)
     return EVG_OK;
 }
 
-int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_status,
-             int32_t* d_scores, void* stream)
+static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_actions, int8_t* d_actions_out, float* d_obs,
+                     float* d_reward, uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream)
 {
-    int rc = check_sim(sim, true);
-    if (rc) return rc;
-    if (!d_actions || !d_obs || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step: actions/obs/reward/done must be non-null");
     evg::StepArgs a;
+    a.agent[0] = agent0;
+    a.agent[1] = agent1;
+    a.actions_out = d_actions_out;
     a.records = (uint32_t*)sim->bound[EVG_BIND_RECORDS];
     a.health = (double*)sim->bound[EVG_BIND_HEALTH];
     a.stats = (unsigned long long*)sim->bound[EVG_BIND_STATS];
@@ -382,6 +382,40 @@ int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward
     sim->launches += 1;
     sim->steps += 1;
     return EVG_OK;
+}
+
+int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_status,
+             int32_t* d_scores, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_actions || !d_obs || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step: actions/obs/reward/done must be non-null");
+    return step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
+}
+
+int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_actions, float* d_obs, float* d_reward,
+                    uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_obs || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step_agents: obs/reward/done must be non-null");
+    const int ag[2] = {agent_p0, agent_p1};
+    bool any_ext = false, any_scripted = false;
+    for (int p = 0; p < 2; ++p) {
+        if (ag[p] != EVG_AGENT_EXTERNAL && ag[p] != EVG_AGENT_RANDOM) return fail(EVG_E_ARG, "unknown agent id %d for player %d", ag[p], p);
+        any_ext |= ag[p] == EVG_AGENT_EXTERNAL;
+        any_scripted |= ag[p] != EVG_AGENT_EXTERNAL;
+    }
+    if (any_ext && !d_actions) return fail(EVG_E_ARG, "evg_step_agents: d_actions is required for EVG_AGENT_EXTERNAL players");
+    const bool fused = sim->use_tpm && sim->cfg.n_nodes <= evg::kAgentMaxNodes;
+    if (!any_scripted || fused)
+        return step_impl(sim, agent_p0, agent_p1, d_actions, any_scripted ? d_actions : nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
+    // not fusable (warp-per-match kernel selected, or a map too large for the register-only agent): agent
+    // kernel(s) into d_actions, then the plain step
+    if (!d_actions) return fail(EVG_E_ARG, "evg_step_agents: d_actions is required when the agents cannot be fused into the step kernel");
+    for (int p = 0; p < 2; ++p)
+        if (ag[p] == EVG_AGENT_RANDOM && (rc = evg_agent_random(sim, d_actions, p, stream))) return rc;
+    return step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
 }
 
 int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done, int8_t* d_actions,

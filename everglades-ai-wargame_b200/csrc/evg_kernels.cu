@@ -642,28 +642,30 @@ __global__ void evg_agent_random_kernel(const __grid_constant__ Tables T, const 
     const int p = player < 0 ? (int)(i % nplayers) : player;
     const uint32_t* rec = records + env * T.rec_words8 * 2;
     const uint32_t turn = rec[kRecTurn] + 1u, episode = rec[kRecEpisode];
-    uint32_t w[16];
+    int8_t* out = actions + (env * 2 + p) * (EVG_MAX_ACTIONS * 2);
+    if (T.n_nodes <= kAgentMaxNodes) {
+        uint32_t rows[EVG_MAX_ACTIONS];
+        agent_random_rows(T.env_base + (uint32_t)env, turn, episode, p, T.n_nodes, T.seed_lo, T.seed_hi, rows);
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-        philox4x32_10(T.env_base + (uint32_t)env, turn, (uint32_t)p | (uint32_t)b << 8, 1u | episode << 8, T.seed_lo, T.seed_hi,
-                      w + 4 * b);
-    // permutations kept as nibbles / bytes in registers: gp holds 12 group ids, nodes up to 32 ids
+        for (int k = 0; k < EVG_MAX_ACTIONS; ++k) reinterpret_cast<uint16_t*>(out)[k] = (uint16_t)rows[k];
+        return;
+    }
+    // larger maps: the same shuffles over byte arrays
+    uint32_t w[8];
+    philox4x32_10(T.env_base + (uint32_t)env, turn, (uint32_t)p, 1u | episode << 8, T.seed_lo, T.seed_hi, w);
+    philox4x32_10(T.env_base + (uint32_t)env, turn, (uint32_t)p | 1u << 8, 1u | episode << 8, T.seed_lo, T.seed_hi, w + 4);
     uint8_t gp[EVG_NUM_GROUPS], np_[EVG_MAX_NODES];
-#pragma unroll
     for (int k = 0; k < EVG_NUM_GROUPS; ++k) gp[k] = (uint8_t)k;
     for (int k = 0; k < T.n_nodes; ++k) np_[k] = (uint8_t)(k + 1);
-    int8_t* out = actions + (env * 2 + p) * (EVG_MAX_ACTIONS * 2);
     for (int k = 0; k < EVG_MAX_ACTIONS; ++k) {
-        const int j = k + (int)__umulhi(w[k], (uint32_t)(EVG_NUM_GROUPS - k));
+        const uint32_t hg = (k & 1) ? w[k >> 1] >> 16 : w[k >> 1] & 0xFFFFu;
+        const uint32_t hn = (k & 1) ? w[4 + (k >> 1)] >> 16 : w[4 + (k >> 1)] & 0xFFFFu;
+        const int j = k + (int)((hg * (uint32_t)(EVG_NUM_GROUPS - k)) >> 16);
         const uint8_t t = gp[k]; gp[k] = gp[j]; gp[j] = t;
-        int node = 0;
-        if (k < T.n_nodes) {
-            const int q = k + (int)__umulhi(w[8 + k], (uint32_t)(T.n_nodes - k));
-            const uint8_t t2 = np_[k]; np_[k] = np_[q]; np_[q] = t2;
-            node = np_[k];
-        }
+        const int q = k + (int)((hn * (uint32_t)(T.n_nodes - k)) >> 16);
+        const uint8_t t2 = np_[k]; np_[k] = np_[q]; np_[q] = t2;
         out[2 * k] = (int8_t)gp[k];
-        out[2 * k + 1] = (int8_t)node;
+        out[2 * k + 1] = (int8_t)np_[k];
     }
 }
 

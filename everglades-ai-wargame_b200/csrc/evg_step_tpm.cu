@@ -196,8 +196,9 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 
     // this turn's action rows (7 words per match), requested before the records so the latencies overlap
     uint32_t aw[7];
+    const bool ext_rows = A.agent[0] == EVG_AGENT_EXTERNAL || A.agent[1] == EVG_AGENT_EXTERNAL;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) aw[k] = valid ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
+    for (int k = 0; k < 7; ++k) aw[k] = (valid && ext_rows) ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
 
     // ---- cooperative, coalesced load of the warp's records into the per-thread rows
     {
@@ -224,13 +225,30 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 
         // ---- action decode + validation, server.py:218-271 (rows in order; first valid row per group wins)
         {
+            // rows of scripted players are generated here (agents/State_Machine/random_actions.py:38-46, tape
+            // domain 1) instead of being read: no action buffer traffic, no second kernel
+            uint32_t rows[2 * EVG_MAX_ACTIONS];
+#pragma unroll
+            for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) rows[r] = (aw[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+            if (A.agent[0] != EVG_AGENT_EXTERNAL || A.agent[1] != EVG_AGENT_EXTERNAL) {
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+                    if (A.agent[pl] == EVG_AGENT_RANDOM)
+                        agent_random_rows(S.env_base + (uint32_t)env, turn, episode, pl, n_nodes, S.seed_lo, S.seed_hi,
+                                          rows + pl * EVG_MAX_ACTIONS);
+                if (A.actions_out) {
+                    uint32_t* ao = reinterpret_cast<uint32_t*>(A.actions_out) + env * 7;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) ao[k] = rows[2 * k] | rows[2 * k + 1] << 16;
+                }
+            }
             // all 14 rows are decoded and looked up first (independent shared-memory reads in flight together:
             // accepting a row changes neither the group's location nor its moving flag), then resolved in order
             int Lr[2 * EVG_MAX_ACTIONS];
             uint32_t dr[2 * EVG_MAX_ACTIONS], nr[2 * EVG_MAX_ACTIONS];
 #pragma unroll
             for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) {
-                const uint32_t a = (aw[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+                const uint32_t a = rows[r];
                 const int ag = (int)(int8_t)(a & 0xFFu);
                 int an = (int)(int8_t)(a >> 8);
                 const int pl = r >= EVG_MAX_ACTIONS ? 1 : 0;

@@ -142,6 +142,29 @@ class BatchedEvergladesEnv:
                                        self._stream()))
         return self.obs, self.reward, self.done, {"status": self.status, "scores": self.scores}
 
+    def step_agents(self, agent0=_capi.AGENT_RANDOM, agent1=_capi.AGENT_RANDOM, actions=None, want_actions=False):
+        """One turn with scripted opponents fused into the step kernel (evg_step_agents).
+
+        agentN: _capi.AGENT_EXTERNAL (rows of that player are taken from `actions`) or _capi.AGENT_RANDOM.
+        With both players scripted and want_actions=False the turn is a single launch that reads no action
+        buffer; want_actions=True also writes the generated rows into the returned info["actions"]."""
+        if not self._is_reset:
+            raise RuntimeError("call reset() before step()")
+        ext = agent0 == _capi.AGENT_EXTERNAL or agent1 == _capi.AGENT_EXTERNAL
+        aptr = None
+        if ext:
+            aptr = C.c_void_p(self._as_actions(actions).data_ptr())
+        elif want_actions:
+            aptr = C.c_void_p(self._actions.data_ptr())
+        _capi.check(self._lib.evg_step_agents(self._h, int(agent0), int(agent1), aptr, C.c_void_p(self.obs.data_ptr()),
+                                              C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                              C.c_void_p(self.status.data_ptr()), C.c_void_p(self.scores.data_ptr()),
+                                              self._stream()))
+        info = {"status": self.status, "scores": self.scores}
+        if aptr is not None:
+            info["actions"] = self._actions
+        return self.obs, self.reward, self.done, info
+
     # ------------------------------------------------------------------ host-buffer path (end-to-end)
     def host_buffers(self):
         """Pinned host arrays for step_host: actions int8[N,2,7,2] in; obs, reward, done out."""

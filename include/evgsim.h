@@ -188,6 +188,17 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
 int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done,
              uint8_t* d_status, int32_t* d_scores, void* stream);
 
+/* where a player's action rows come from in evg_step_agents */
+#define EVG_AGENT_EXTERNAL 0 /* the caller's rows in d_actions */
+#define EVG_AGENT_RANDOM 1   /* on-device random_actions agent (agents/State_Machine/random_actions.py:38-46) */
+
+/* evg_step with scripted opponents fused into the step kernel: rows of players whose agent is not
+ * EVG_AGENT_EXTERNAL are generated on the device (and written to d_actions if it is non-NULL); rows of
+ * EXTERNAL players are read from d_actions (then it must be non-NULL).  With both players scripted a
+ * whole self-play turn is ONE kernel launch and no action buffer is touched. */
+int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_actions, float* d_obs, float* d_reward,
+                    uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream);
+
 /* Same turn through HOST buffers: H2D of the actions, the step, D2H of obs/reward/done, all
  * queued on `stream` (pinned host memory makes them truly asynchronous).  The device staging
  * arrays are the caller's (same shapes as evg_step). */

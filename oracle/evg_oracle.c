@@ -450,25 +450,29 @@ int evo_step(const EvgConfig* c, EvgEnvState* s, uint64_t seed, uint64_t env, co
 void evo_agent_random(const EvgConfig* c, uint64_t seed, uint64_t env, uint32_t episode, int turn, int player,
                       int32_t* rows /*[7][2]*/)
 {
-    uint32_t w[16], ctr[4] = {(uint32_t)env, (uint32_t)turn, 0, 1u /* DOMAIN_AGENT_RANDOM */ | episode << 8},
-                    key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    for (int b = 0; b < 4; ++b) {
+    /* 16 tape values of 16 bits: halves of the words of Philox blocks (player | 0<<8) and (player | 1<<8);
+       group step k uses half k, node step k uses half 8 + k */
+    uint32_t w[8], ctr[4] = {(uint32_t)env, (uint32_t)turn, 0, 1u /* DOMAIN_AGENT_RANDOM */ | episode << 8},
+                   key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int b = 0; b < 2; ++b) {
         ctr[2] = (uint32_t)player | (uint32_t)b << 8;
         philox4x32_10(ctr, key, w + 4 * b);
     }
     int gp[NG], np_[EVG_MAX_NODES];
     for (int i = 0; i < NG; ++i) gp[i] = i;
     for (int i = 0; i < c->n_nodes; ++i) np_[i] = i + 1;
-    for (int i = 0; i < EVG_MAX_ACTIONS; ++i) {
-        int j = i + (int)(((uint64_t)w[i] * (uint32_t)(NG - i)) >> 32), t = gp[i];
-        gp[i] = gp[j]; gp[j] = t;
+    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) {
+        uint32_t hg = (k & 1) ? w[k >> 1] >> 16 : w[k >> 1] & 0xFFFFu;
+        uint32_t hn = (k & 1) ? w[4 + (k >> 1)] >> 16 : w[4 + (k >> 1)] & 0xFFFFu;
+        int j = k + (int)((hg * (uint32_t)(NG - k)) >> 16), t = gp[k];
+        gp[k] = gp[j]; gp[j] = t;
         int nn = c->n_nodes;
-        if (i < nn) {
-            int k = i + (int)(((uint64_t)w[8 + i] * (uint32_t)(nn - i)) >> 32), t2 = np_[i];
-            np_[i] = np_[k]; np_[k] = t2;
+        if (k < nn) {
+            int q = k + (int)((hn * (uint32_t)(nn - k)) >> 16), t2 = np_[k];
+            np_[k] = np_[q]; np_[q] = t2;
         }
-        rows[2 * i] = gp[i];
-        rows[2 * i + 1] = i < nn ? np_[i] : 0;
+        rows[2 * k] = gp[k];
+        rows[2 * k + 1] = k < nn ? np_[k] : 0;
     }
 }
 

@@ -257,3 +257,35 @@ def test_warp_per_match_kernel_still_matches_oracle(evg, eo, cfg, monkeypatch):
     monkeypatch.setenv("EVG_STEP_KERNEL", "warp")
     rng = np.random.default_rng(31)
     run_against_oracle(evg, eo, cfg, 1024, 150, seed=19, first=7, make_actions=lambda s: adjacent_actions(rng, s, cfg))
+
+
+def test_fused_agents_equal_agent_kernel_plus_step(evg, eo, cfg):
+    """evg_step_agents (rows generated inside the step kernel) == evg_agent_random + evg_step == oracle."""
+    n = 640
+    cfg.auto_reset = 1
+    cfg.turn_limit = 60
+    try:
+        env = evg.BatchedEvergladesEnv(n, seed=99, config=cfg, auto_reset=1, env_id_offset=11)
+        ora = eo.OracleBatch(cfg, n, seed=99, first=11)
+        env.reset()
+        ora.reset()
+        for t in range(130):
+            want = np.zeros((n, 2, 7, 2), dtype=np.int8)
+            for i in range(n):
+                for p in range(2):
+                    want[i, p] = eo.agent_random(cfg, 99, 11 + i, int(ora.states[i]["episode"]), int(ora.states[i]["turn"]) + 1, p)
+            if t % 3 == 0:    # both scripted, rows reported
+                obs, rew, done, info = env.step_agents(want_actions=True)
+                assert np.array_equal(info["actions"].cpu().numpy(), want), t
+            elif t % 3 == 1:  # both scripted, nothing written
+                obs, rew, done, info = env.step_agents()
+            else:             # player 0 external, player 1 scripted
+                obs, rew, done, info = env.step_agents(evg._capi.AGENT_EXTERNAL, evg._capi.AGENT_RANDOM, actions=want.copy())
+            oobs, orew, odone = ora.step(want)
+            assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+            assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
+            assert np.array_equal(done.cpu().numpy(), odone), t
+        assert_states_equal(env.get_state(), ora.states, "end")
+    finally:
+        cfg.auto_reset = 0
+        cfg.turn_limit = 150
