@@ -119,7 +119,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "elapsed_s": el,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,8 +196,25 @@ def ncu_traffic(envs_per_gpu):
 
 
 # ------------------------------------------------------------------------------------------------
+def _emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner,
+    build messages) was diverted to stderr by _quiet_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout() -> None:
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -321,7 +338,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             rate, threads, sample, _ = cpu_oracle_rate(args.cpu_seconds, seed=args.seed)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

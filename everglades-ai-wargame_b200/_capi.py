@@ -20,8 +20,8 @@ ABI_VERSION = 1
 
 AUTORESET_OFF, AUTORESET_TERMINAL, AUTORESET_NEXT = 0, 1, 2
 STATUS_IN_PROGRESS, STATUS_TIME_EXPIRED, STATUS_BASE_CAPTURE, STATUS_ANNIHILATION = 0, 1, 2, 3
-AGENT_EXTERNAL, AGENT_RANDOM = 0, 1
-BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_COUNT = 0, 1, 2, 3, 4
+AGENT_EXTERNAL, AGENT_RANDOM, AGENT_BASE_RUSH, AGENT_SWARM = 0, 1, 2, 3
+BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_AGENTS, BIND_COUNT = 0, 1, 2, 3, 4, 5
 
 _N1 = MAX_NODES + 1
 
@@ -91,6 +91,7 @@ class EvgLayout(C.Structure):
         ("health_bytes", C.c_int64),
         ("stats_bytes", C.c_int64),
         ("tables_bytes", C.c_int64),
+        ("agents_bytes", C.c_int64),
     ]
 
 
@@ -151,6 +152,7 @@ SYMBOLS = [
     ("evg_import_state", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     ("evg_episode_stats", C.c_int, [_P, C.POINTER(EvgEpisodeStats), _P]),
     ("evg_agent_random", C.c_int, [_P, _P, C.c_int32, _P]),
+    ("evg_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_launch_count", C.c_int64, [_P]),
     ("evg_last_error", C.c_char_p, []),
     ("evg_abi_version", C.c_int, []),

@@ -140,6 +140,20 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.has_small_groups = small;
     t.n_big = n_big;
     t.hist_words = (max_units + 1) / 2 + 1;
+    for (int p = 0; p < EVG_NUM_PLAYERS; ++p) {
+        const int enemy = start[1 - p];
+        t.base_own[p] = (uint8_t)(p ? c.p1_node_map[enemy] : enemy);
+        for (int a = 1; a <= c.n_nodes; ++a) {  // a = own-numbered node
+            const int real = p ? c.p1_node_map[a] : a;
+            int best = 0;
+            for (int b = 1; b <= c.n_nodes; ++b)
+                if (c.edge_distance[real][b]) {
+                    const int own = p ? c.p1_node_map[b] : b;
+                    if (own > best) best = own;
+                }
+            t.maxnb_own[p][a] = (uint8_t)best;
+        }
+    }
     // node state after game_init's capture() at turn 0 (server.py:206,744-745,763-765)
     for (int n = 1; n <= c.n_nodes; ++n) {
         int cs = 0, cb = c.node_team_start[n];
@@ -289,6 +303,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.records_bytes = n_envs * L.record_bytes;
     L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
     L.stats_bytes = evg::ST_COUNT * 8;
+    L.agents_bytes = n_envs * 16;
     L.tables_bytes = (int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * evg::kLossD * 8;
     *out = s;
     return EVG_OK;
@@ -350,6 +365,7 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream)
     cudaError_t e;
     if (!d_mask) {
         if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_STATS], 0, evg::ST_COUNT * 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(stats)");
+        if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_AGENTS], 0, (size_t)sim->n_envs * 16, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agent state)");
         sim->steps = 0;
     }
     e = evg::launch_reset(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], d_mask, d_obs,
@@ -401,20 +417,21 @@ int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_a
     if (!d_obs || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step_agents: obs/reward/done must be non-null");
     const int ag[2] = {agent_p0, agent_p1};
     bool any_ext = false, any_scripted = false;
+    bool fusable = true;
     for (int p = 0; p < 2; ++p) {
-        if (ag[p] != EVG_AGENT_EXTERNAL && ag[p] != EVG_AGENT_RANDOM) return fail(EVG_E_ARG, "unknown agent id %d for player %d", ag[p], p);
+        if (ag[p] < EVG_AGENT_EXTERNAL || ag[p] > EVG_AGENT_SWARM) return fail(EVG_E_ARG, "unknown agent id %d for player %d", ag[p], p);
         any_ext |= ag[p] == EVG_AGENT_EXTERNAL;
         any_scripted |= ag[p] != EVG_AGENT_EXTERNAL;
+        fusable &= ag[p] == EVG_AGENT_EXTERNAL || ag[p] == EVG_AGENT_RANDOM;
     }
     if (any_ext && !d_actions) return fail(EVG_E_ARG, "evg_step_agents: d_actions is required for EVG_AGENT_EXTERNAL players");
-    const bool fused = sim->use_tpm && sim->cfg.n_nodes <= evg::kAgentMaxNodes;
+    const bool fused = fusable && sim->use_tpm && sim->cfg.n_nodes <= evg::kAgentMaxNodes;
     if (!any_scripted || fused)
         return step_impl(sim, agent_p0, agent_p1, d_actions, any_scripted ? d_actions : nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
     // not fusable (warp-per-match kernel selected, or a map too large for the register-only agent): agent
     // kernel(s) into d_actions, then the plain step
     if (!d_actions) return fail(EVG_E_ARG, "evg_step_agents: d_actions is required when the agents cannot be fused into the step kernel");
-    for (int p = 0; p < 2; ++p)
-        if (ag[p] == EVG_AGENT_RANDOM && (rc = evg_agent_random(sim, d_actions, p, stream))) return rc;
+    if ((rc = evg_agents(sim, agent_p0, agent_p1, d_actions, stream))) return rc;
     return step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
 }
 
@@ -490,6 +507,28 @@ int evg_agent_random(EvgSim* sim, int8_t* d_actions, int32_t player, void* strea
     cudaError_t e = evg::launch_agent_random(sim->tables, (const uint32_t*)sim->bound[EVG_BIND_RECORDS], d_actions, player, sim->n_envs,
                                              (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_agent_random_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
+int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_actions, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_actions) return fail(EVG_E_ARG, "evg_agents: d_actions is null");
+    const int ag[2] = {agent_p0, agent_p1};
+    for (int p = 0; p < 2; ++p) {
+        if (ag[p] < EVG_AGENT_EXTERNAL || ag[p] > EVG_AGENT_SWARM) return fail(EVG_E_ARG, "unknown agent id %d for player %d", ag[p], p);
+        if (ag[p] == EVG_AGENT_RANDOM && sim->cfg.n_nodes > evg::kAgentMaxNodes) {  // byte-array variant lives in evg_agent_random
+            if ((rc = evg_agent_random(sim, d_actions, p, stream))) return rc;
+        }
+    }
+    const int a0 = (ag[0] == EVG_AGENT_RANDOM && sim->cfg.n_nodes > evg::kAgentMaxNodes) ? EVG_AGENT_EXTERNAL : ag[0];
+    const int a1 = (ag[1] == EVG_AGENT_RANDOM && sim->cfg.n_nodes > evg::kAgentMaxNodes) ? EVG_AGENT_EXTERNAL : ag[1];
+    if (a0 == EVG_AGENT_EXTERNAL && a1 == EVG_AGENT_EXTERNAL) return EVG_OK;
+    cudaError_t e = evg::launch_agents(sim->tables, (const uint32_t*)sim->bound[EVG_BIND_RECORDS], (uint2*)sim->bound[EVG_BIND_AGENTS], d_actions,
+                                       a0, a1, sim->n_envs, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_agents_kernel launch");
     sim->launches += 1;
     return EVG_OK;
 }

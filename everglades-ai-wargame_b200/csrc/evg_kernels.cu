@@ -670,6 +670,87 @@ __global__ void evg_agent_random_kernel(const __grid_constant__ Tables T, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Observation-driven scripted agents, one thread per (match, player); the "observation" they read is
+// the resident record (location / in-transit flag of the player's groups, in the player's own node
+// numbering), which is what obs[45+5g], obs[45+5g+3] hold.  Agent state: uint2 per (match, player),
+// .x base_rushV1 {bit0 started, group_num[4:8), node_num[8:16)}, .y SwarmAgent's attack list as nibbles;
+// zero = a fresh agent.  Same functions as evo_agent_base_rush / evo_agent_swarm (oracle/evg_oracle.c),
+// which are checked against the reference's own Python agents (tests/golden/agents_v1.npz).
+// ---------------------------------------------------------------------------------------------
+__global__ void evg_agents_kernel(const __grid_constant__ Tables T, const uint32_t* records, uint2* agent_state, int8_t* actions,
+                                  int agent0, int agent1, int64_t n_envs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_envs * 2) return;
+    const int64_t env = i >> 1;
+    const int p = (int)(i & 1);
+    const int kind = p ? agent1 : agent0;
+    if (kind == EVG_AGENT_EXTERNAL) return;
+    const uint32_t* rec = records + env * T.rec_words8 * 2;
+    const uint32_t turn = rec[kRecTurn] + 1u, episode = rec[kRecEpisode];
+    uint16_t* out = reinterpret_cast<uint16_t*>(actions + (env * 2 + p) * (EVG_MAX_ACTIONS * 2));
+    uint32_t rows[EVG_MAX_ACTIONS];
+    if (kind == EVG_AGENT_RANDOM) {  // maps of <= 15 nodes (checked by the host)
+        agent_random_rows(T.env_base + (uint32_t)env, turn, episode, p, T.n_nodes, T.seed_lo, T.seed_hi, rows);
+    } else if (kind == EVG_AGENT_BASE_RUSH) {
+        // base_rushV1.get_action, agents/State_Machine/base_rush_v1.py:62-111
+        uint2 st = agent_state[env * 2 + p];
+        const bool started = st.x & 1u;
+        uint32_t gnum = started ? (st.x >> 4) & 15u : 1u, nnum = started ? (st.x >> 8) & 255u : 2u;
+#pragma unroll
+        for (int k = 0; k < EVG_MAX_ACTIONS; ++k) {
+            rows[k] = 0;
+            if (started) {  // the first call only blows the turn (:73-76)
+                const uint32_t loc = rec[2 * (p * EVG_NUM_GROUPS + k)] & W0_LOC_MASK;  // GROUP k's location (:86-88)
+                const uint32_t own = p ? (uint32_t)T.p1_map[loc] : loc;
+                if (own != T.base_own[p]) {
+                    rows[k] = gnum | nnum << 8;
+                    gnum = gnum + 1 == EVG_NUM_GROUPS ? 0u : gnum + 1;
+                    if (gnum == 0) nnum = nnum % (uint32_t)T.n_nodes + 1u;
+                }
+            }
+        }
+        st.x = 1u | gnum << 4 | nnum << 8;
+        agent_state[env * 2 + p] = st;
+    } else {
+        // SwarmAgent.get_action, agents/State_Machine/swarm_agent.py:79-102
+        uint2 st = agent_state[env * 2 + p];
+        uint32_t lst = st.y ? st.y : 0xBA875421u;  // ATTACK_LIST [1,2,4,5,7,8,10,11], :24
+        uint32_t w[4];
+        philox4x32_10(T.env_base + (uint32_t)env, turn, (uint32_t)p, 2u | episode << 8, T.seed_lo, T.seed_hi, w);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {  // np.random.shuffle: i = 7..1, j uniform in [0, i]
+            const int ii = 7 - k;
+            const uint32_t h = (k & 1) ? w[k >> 1] >> 16 : w[k >> 1] & 0xFFFFu;
+            const int j = (int)((h * (uint32_t)(ii + 1)) >> 16);
+            const uint32_t d = ((lst >> (4 * ii)) ^ (lst >> (4 * j))) & 15u;
+            lst ^= d << (4 * ii) | d << (4 * j);
+        }
+        st.y = lst;
+        agent_state[env * 2 + p] = st;
+#pragma unroll
+        for (int k = 0; k < EVG_MAX_ACTIONS; ++k) rows[k] = 0u | 1u << 8;  // default rows [0, 1], :81-82
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = (lst >> (4 * k)) & 15u;
+            const uint32_t w0 = rec[2 * (p * EVG_NUM_GROUPS + x)];
+            if (n < EVG_MAX_ACTIONS && !(w0 & W0_MOVING)) {
+                const uint32_t loc = w0 & W0_LOC_MASK;
+                const uint32_t own = p ? (uint32_t)T.p1_map[loc] : loc;
+                const uint32_t row = x | (uint32_t)T.maxnb_own[p][own] << 8;
+#pragma unroll
+                for (int q = 0; q < EVG_MAX_ACTIONS; ++q)
+                    if (q == n) rows[q] = row;
+                ++n;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) out[k] = (uint16_t)rows[k];
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 // DemoMap's node count gets a compile-time instantiation; any other map runs the generic one.
@@ -725,6 +806,14 @@ cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t
     const int64_t n = n_envs * (player < 0 ? 2 : 1);
     if (n <= 0) return cudaSuccess;
     evg_agent_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(t, records, actions, player, n_envs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_agents(const Tables& t, const uint32_t* records, uint2* agent_state, int8_t* actions, int agent0, int agent1,
+                          int64_t n_envs, cudaStream_t stream)
+{
+    if (n_envs <= 0) return cudaSuccess;
+    evg_agents_kernel<<<(unsigned)((n_envs * 2 + 255) / 256), 256, 0, stream>>>(t, records, agent_state, actions, agent0, agent1, n_envs);
     return cudaGetLastError();
 }
 

@@ -70,6 +70,7 @@ class BatchedEvergladesEnv:
             self._health = torch.empty(lay.health_bytes // 8, dtype=torch.float64, device=self.device)
             self._stats = torch.zeros(lay.stats_bytes // 8, dtype=torch.int64, device=self.device)
             self._tables = torch.zeros(lay.tables_bytes // 8, dtype=torch.float64, device=self.device)
+            self._agents = torch.zeros(lay.agents_bytes // 4, dtype=torch.int32, device=self.device)
             self.obs = torch.empty((N, 2, self.obs_len), dtype=torch.float32, device=self.device)
             self.reward = torch.empty((N, 2), dtype=torch.float32, device=self.device)
             self.done = torch.empty((N,), dtype=torch.uint8, device=self.device)
@@ -77,7 +78,7 @@ class BatchedEvergladesEnv:
             self.scores = torch.empty((N, 2), dtype=torch.int32, device=self.device)
             self._actions = torch.zeros((N, 2, _capi.MAX_ACTIONS, 2), dtype=torch.int8, device=self.device)
         ptrs = (C.c_void_p * _capi.BIND_COUNT)(self._records.data_ptr(), self._health.data_ptr(), self._stats.data_ptr(),
-                                               self._tables.data_ptr())
+                                               self._tables.data_ptr(), self._agents.data_ptr())
         _capi.check(self._lib.evg_bind(self._h, ptrs, _capi.BIND_COUNT))
         self._host = None
         self._is_reset = False
@@ -154,8 +155,8 @@ class BatchedEvergladesEnv:
         aptr = None
         if ext:
             aptr = C.c_void_p(self._as_actions(actions).data_ptr())
-        elif want_actions:
-            aptr = C.c_void_p(self._actions.data_ptr())
+        elif want_actions or not {int(agent0), int(agent1)} <= {_capi.AGENT_EXTERNAL, _capi.AGENT_RANDOM}:
+            aptr = C.c_void_p(self._actions.data_ptr())  # observation-driven agents run as their own kernel
         _capi.check(self._lib.evg_step_agents(self._h, int(agent0), int(agent1), aptr, C.c_void_p(self.obs.data_ptr()),
                                               C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
                                               C.c_void_p(self.status.data_ptr()), C.c_void_p(self.scores.data_ptr()),
@@ -211,6 +212,13 @@ class BatchedEvergladesEnv:
         """random_actions agent (agents/State_Machine/random_actions.py:38-46) for `player` (-1 = both)."""
         out = self._actions if out is None else out
         _capi.check(self._lib.evg_agent_random(self._h, C.c_void_p(out.data_ptr()), int(player), self._stream()))
+        return out
+
+    def agent_actions(self, agent0, agent1, out=None):
+        """Rows of the scripted agents (_capi.AGENT_RANDOM / AGENT_BASE_RUSH / AGENT_SWARM) for both players into an
+        int8 [N,2,7,2] tensor; AGENT_EXTERNAL players' rows are left as they are."""
+        out = self._actions if out is None else out
+        _capi.check(self._lib.evg_agents(self._h, int(agent0), int(agent1), C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
     # ------------------------------------------------------------------ snapshots

@@ -134,13 +134,15 @@ typedef struct EvgLayout {
     int64_t health_bytes;  /* = n_envs * health_slots * 8       (bind slot EVG_BIND_HEALTH)  */
     int64_t stats_bytes;   /* episode statistics accumulators   (bind slot EVG_BIND_STATS)   */
     int64_t tables_bytes;  /* derived lookup tables, filled by evg_bind (bind slot EVG_BIND_TABLES) */
+    int64_t agents_bytes;  /* scripted-agent state, 16 B per match (bind slot EVG_BIND_AGENTS)     */
 } EvgLayout;
 
 #define EVG_BIND_RECORDS 0
 #define EVG_BIND_HEALTH 1
 #define EVG_BIND_STATS 2
 #define EVG_BIND_TABLES 3
-#define EVG_BIND_COUNT 4
+#define EVG_BIND_AGENTS 4
+#define EVG_BIND_COUNT 5
 
 /* Episode statistics accumulated on the device by evg_step (matches that ended). */
 typedef struct EvgEpisodeStats {
@@ -191,6 +193,8 @@ int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward
 /* where a player's action rows come from in evg_step_agents */
 #define EVG_AGENT_EXTERNAL 0 /* the caller's rows in d_actions */
 #define EVG_AGENT_RANDOM 1   /* on-device random_actions agent (agents/State_Machine/random_actions.py:38-46) */
+#define EVG_AGENT_BASE_RUSH 2 /* base_rushV1 (agents/State_Machine/base_rush_v1.py:62-111); keeps its counters per match */
+#define EVG_AGENT_SWARM 3    /* SwarmAgent (agents/State_Machine/swarm_agent.py:79-102); keeps its attack list per match */
 
 /* evg_step with scripted opponents fused into the step kernel: rows of players whose agent is not
  * EVG_AGENT_EXTERNAL are generated on the device (and written to d_actions if it is non-NULL); rows of
@@ -216,6 +220,11 @@ int evg_episode_stats(EvgSim* sim, EvgEpisodeStats* host_out, void* stream);
 /* On-device scripted opponents (agents/State_Machine, Python files), writing int8 [n_envs][2][7][2]
  * action rows for `player` (0, 1, or -1 = both).  See DESIGN.md §7 for their tape. */
 int evg_agent_random(EvgSim* sim, int8_t* d_actions, int32_t player, void* stream);
+
+/* Action rows of the scripted agents for both players (EVG_AGENT_EXTERNAL players are left untouched) into
+ * int8 [n_envs][2][7][2].  base_rushV1 / SwarmAgent carry per-match state across turns and matches (like the
+ * reference's agent objects); evg_reset(sim, NULL, ...) makes all of them fresh agents again. */
+int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_actions, void* stream);
 
 /* Number of kernels this library has launched since creation (bench.py's gpu_launches). */
 int64_t evg_launch_count(const EvgSim* sim);

@@ -476,6 +476,69 @@ void evo_agent_random(const EvgConfig* c, uint64_t seed, uint64_t env, uint32_t 
     }
 }
 
+/* own-numbering helpers for the observation-driven agents: an agent sees node ids through its player's map */
+static int own_id(const EvgConfig* c, int player, int real) { return player == 1 ? c->p1_node_map[real] : real; }
+
+/* base_rushV1.get_action (agents/State_Machine/base_rush_v1.py:62-111).  State word: bit0 = the blown first
+ * turn is over (:73-76), bits 4-7 group_num, bits 8-15 node_num (initially 1 and 2, :55-56).  The agent keeps
+ * its counters across matches, exactly like the reference object does.  Quirk kept: row i is issued when GROUP i
+ * (not group_num) is away from node 11 — the enemy base in the player's own numbering (:86-88). */
+void evo_agent_base_rush(const EvgConfig* c, const EvgEnvState* s, uint32_t* state, int player, int32_t* rows /*[7][2]*/)
+{
+    int started = *state & 1u, gnum = started ? (*state >> 4) & 15 : 1, nnum = started ? (*state >> 8) & 255 : 2;
+    int enemy_base = 0;
+    for (int x = 1; x <= c->n_nodes; ++x)
+        if (c->node_team_start[x] == 1 - player) enemy_base = own_id(c, player, x);
+    for (int i = 0; i < 2 * EVG_MAX_ACTIONS; ++i) rows[i] = 0;
+    if (started) { /* act_all_cycle, :79-93 */
+        for (int i = 0; i < EVG_MAX_ACTIONS; ++i) {
+            if (own_id(c, player, s->groups[player][i].location) != enemy_base) {
+                rows[2 * i] = gnum;
+                rows[2 * i + 1] = nnum;
+                gnum = (gnum + 1) % NG;
+                int nodetest = nnum % c->n_nodes + 1;
+                if (gnum == 0) nnum = nodetest;
+            }
+        }
+    }
+    *state = 1u | (uint32_t)gnum << 4 | (uint32_t)nnum << 8;
+}
+
+/* SwarmAgent.get_action (agents/State_Machine/swarm_agent.py:79-102).  State word: the module-level
+ * ATTACK_LIST [1,2,4,5,7,8,10,11] (:24), shuffled IN PLACE on every call (:86-87) and therefore carried from
+ * turn to turn, as 8 nibbles (0 = not started).  The shuffle is numpy's Fisher-Yates with the tape of
+ * oracle/tape.py:swarm_shuffle.  Each listed group that is not in transit is sent to the highest-numbered
+ * neighbour of where it stands (own numbering), up to 7 rows; unused rows stay [0, 1] (:81-82). */
+void evo_agent_swarm(const EvgConfig* c, const EvgEnvState* s, uint32_t* state, uint64_t seed, uint64_t env, int player,
+                     int32_t* rows /*[7][2]*/)
+{
+    uint32_t lst = *state ? *state : 0xBA875421u;
+    uint32_t w[4], ctr[4] = {(uint32_t)env, (uint32_t)(s->turn + 1), (uint32_t)player, 2u | (uint32_t)s->episode << 8},
+                   key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    philox4x32_10(ctr, key, w);
+    for (int k = 0, i = 7; i >= 1; ++k, --i) {
+        uint32_t h = (k & 1) ? w[k >> 1] >> 16 : w[k >> 1] & 0xFFFFu;
+        int j = (int)((h * (uint32_t)(i + 1)) >> 16);
+        uint32_t a = (lst >> (4 * i)) & 15u, b = (lst >> (4 * j)) & 15u, d = a ^ b;
+        lst ^= d << (4 * i) | d << (4 * j);
+    }
+    *state = lst;
+    for (int i = 0; i < EVG_MAX_ACTIONS; ++i) { rows[2 * i] = 0; rows[2 * i + 1] = 1; }
+    int n = 0;
+    for (int k = 0; k < 8 && n < EVG_MAX_ACTIONS; ++k) {
+        int x = (lst >> (4 * k)) & 15;
+        const EvgGroupState* G = &s->groups[player][x];
+        if (!G->moving) {
+            int best = 0; /* max(NODE_CONNECTIONS[pos]) in the player's own numbering */
+            for (int b = 1; b <= c->n_nodes; ++b)
+                if (c->edge_distance[G->location][b] && own_id(c, player, b) > best) best = own_id(c, player, b);
+            rows[2 * n] = x;
+            rows[2 * n + 1] = best;
+            ++n;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ batch driver (CPU baseline)
  * Runs matches [first, first+count) for n_turns turns with both players random_actions, with
  * in-place reset on done (what the GPU arm does with EVG_AUTORESET_TERMINAL); returns the number

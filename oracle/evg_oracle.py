@@ -50,6 +50,10 @@ def lib():
         L.evo_run_random.restype = C.c_int64
         L.evo_step_batch.argtypes = [C.POINTER(_capi.EvgConfig), P, C.c_int64, C.c_uint64, C.c_int64, P, P, P, P, P, P]
         L.evo_step_batch.restype = None
+        L.evo_agent_base_rush.argtypes = [C.POINTER(_capi.EvgConfig), P, P, C.c_int, P]
+        L.evo_agent_base_rush.restype = None
+        L.evo_agent_swarm.argtypes = [C.POINTER(_capi.EvgConfig), P, P, C.c_uint64, C.c_uint64, C.c_int, P]
+        L.evo_agent_swarm.restype = None
         L.evo_philox.argtypes = [P, P, P]
         L.evo_philox.restype = None
         assert L.evo_sizeof_config() == C.sizeof(_capi.EvgConfig)
@@ -134,6 +138,27 @@ def agent_random(cfg, seed, env_id, episode, turn, player):
     lib().evo_agent_random(C.byref(cfg), int(seed), int(env_id), int(episode), int(turn), int(player),
                            rows.ctypes.data_as(C.c_void_p))
     return rows
+
+
+class ScriptedAgents:
+    """Per-match state of the observation-driven scripted agents (one uint32 per (match, player, kind))."""
+
+    def __init__(self, n):
+        self.state = np.zeros((n, 2, 2), dtype=np.uint32)  # [..., 0] base_rush, [..., 1] swarm
+
+    def rows(self, kind, cfg, states, seed, first, player):
+        """kind: 'base_rush' | 'swarm'. Returns int8 [n, 7, 2] rows for `player`, advancing the agent state."""
+        n = len(states)
+        out = np.zeros((n, 7, 2), dtype=np.int32)
+        for i in range(n):
+            sp = C.c_void_p(states.ctypes.data + i * states.itemsize)
+            if kind == "base_rush":
+                stp = C.c_void_p(self.state.ctypes.data + (i * 4 + player * 2) * 4)
+                lib().evo_agent_base_rush(C.byref(cfg), sp, stp, player, C.c_void_p(out.ctypes.data + i * 56))
+            else:
+                stp = C.c_void_p(self.state.ctypes.data + (i * 4 + player * 2 + 1) * 4)
+                lib().evo_agent_swarm(C.byref(cfg), sp, stp, int(seed), int(first + i), player, C.c_void_p(out.ctypes.data + i * 56))
+        return out.astype(np.int8)
 
 
 def run_random(cfg, seed, first, count, n_turns):

@@ -29,6 +29,7 @@ MASK = 0xFFFFFFFF
 
 DOMAIN_COMBAT = 0          # combat target draws (server.py:562)
 DOMAIN_AGENT_RANDOM = 1    # on-device random_actions agent
+DOMAIN_AGENT_SWARM = 2     # SwarmAgent's np.random.shuffle (agents/State_Machine/swarm_agent.py:86-87)
 
 
 def philox4x32(ctr, key, rounds: int = 10):
@@ -57,3 +58,22 @@ def combat_word(seed: int, env: int, turn: int, node: int, side: int, gid: int, 
 def combat_draw(seed: int, env: int, turn: int, node: int, side: int, gid: int, j: int, n: int, episode: int = 0) -> int:
     """Value the patched ``np.random.randint(n)`` returns at server.py:562."""
     return (combat_word(seed, env, turn, node, side, gid, j, episode) * int(n)) >> 16
+
+
+def block_halves(seed: int, env: int, turn: int, c2: int, domain: int, episode: int = 0):
+    """The 8 16-bit tape values of one Philox block: low half then high half of each word."""
+    w = philox4x32((env & MASK, turn & MASK, c2 & MASK, domain | (episode & 0xFFFFFF) << 8), (seed & MASK, (seed >> 32) & MASK))
+    out = []
+    for x in w:
+        out += [x & 0xFFFF, x >> 16]
+    return out
+
+
+def swarm_shuffle(lst, seed: int, env: int, turn: int, player: int, episode: int = 0) -> None:
+    """In-place stand-in for the legacy ``np.random.shuffle(temp_list)`` of SwarmAgent.get_action
+    (numpy's Fisher-Yates: for i = n-1 .. 1: j = uniform{0..i}; swap) with j read from the tape."""
+    h = block_halves(seed, env, turn, player, DOMAIN_AGENT_SWARM, episode)
+    n = len(lst)
+    for k, i in enumerate(range(n - 1, 0, -1)):
+        j = (h[k] * (i + 1)) >> 16
+        lst[i], lst[j] = lst[j], lst[i]

@@ -289,3 +289,50 @@ def test_fused_agents_equal_agent_kernel_plus_step(evg, eo, cfg):
     finally:
         cfg.auto_reset = 0
         cfg.turn_limit = 150
+
+
+def test_scripted_agents_match_reference_agent_games(evg, cfg):
+    """Config 3 of BASELINE.json: base_rushV1 vs SwarmAgent.  The device agents + device step reproduce the games
+    the reference's own Python agents played on the reference env (tests/golden/agents_v1.npz), row for row."""
+    from test_agents_cpu import load_agent_games
+    seed, kinds, games = load_agent_games()
+    ids = {"base_rush": evg._capi.AGENT_BASE_RUSH, "swarm": evg._capi.AGENT_SWARM}
+    for i, (kk, g) in enumerate(zip(kinds, games)):
+        env = evg.BatchedEvergladesEnv(1, seed=seed, config=cfg, env_id_offset=i)
+        obs = env.reset().cpu().numpy()
+        assert np.array_equal(obs[0], g["obs"][0].astype(np.float32))
+        for t in range(len(g["done"])):
+            a = env.agent_actions(ids[kk[0]], ids[kk[1]])
+            assert np.array_equal(a.cpu().numpy()[0], g["actions"][t]), (i, kk, t)
+            obs, rew, done, _ = env.step(a)
+            assert np.array_equal(obs.cpu().numpy()[0], g["obs"][t + 1].astype(np.float32)), (i, t)
+            assert np.array_equal(rew.cpu().numpy()[0], g["reward"][t].astype(np.float32)) and int(done[0]) == g["done"][t]
+
+
+def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg):
+    """65,536-style run in small: base_rush vs swarm with in-place auto-reset over several matches; agent state
+    persists across matches exactly like the oracle's (and the reference's agent objects)."""
+    n = 512
+    cfg.auto_reset = 1
+    try:
+        env = evg.BatchedEvergladesEnv(n, seed=41, config=cfg, auto_reset=1, env_id_offset=3)
+        ora = eo.OracleBatch(cfg, n, seed=41, first=3)
+        ag = eo.ScriptedAgents(n)
+        env.reset()
+        ora.reset()
+        for t in range(230):
+            want = np.stack([ag.rows("base_rush", cfg, ora.states, 41, 3, 0), ag.rows("swarm", cfg, ora.states, 41, 3, 1)], axis=1)
+            if t % 2:
+                obs, rew, done, info = env.step_agents(evg._capi.AGENT_BASE_RUSH, evg._capi.AGENT_SWARM, want_actions=True)
+                assert np.array_equal(info["actions"].cpu().numpy(), want), t
+            else:
+                a = env.agent_actions(evg._capi.AGENT_BASE_RUSH, evg._capi.AGENT_SWARM)
+                assert np.array_equal(a.cpu().numpy(), want), t
+                obs, rew, done, info = env.step(a)
+            oobs, orew, odone = ora.step(want)
+            assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+            assert np.array_equal(done.cpu().numpy(), odone), t
+        assert env.episode_stats()["episodes"] >= 2 * n
+        assert_states_equal(env.get_state(), ora.states, "end")
+    finally:
+        cfg.auto_reset = 0
