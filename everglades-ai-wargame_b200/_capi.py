@@ -153,6 +153,8 @@ SYMBOLS = [
     ("evg_episode_stats", C.c_int, [_P, C.POINTER(EvgEpisodeStats), _P]),
     ("evg_agent_random", C.c_int, [_P, _P, C.c_int32, _P]),
     ("evg_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    ("evg_decode_dqn", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    ("evg_decode_indices", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     ("evg_launch_count", C.c_int64, [_P]),
     ("evg_last_error", C.c_char_p, []),
     ("evg_abi_version", C.c_int, []),

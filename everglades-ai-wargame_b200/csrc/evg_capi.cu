@@ -533,6 +533,28 @@ int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_action
     return EVG_OK;
 }
 
+int evg_decode_dqn(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int8_t* d_actions, void* stream)
+{
+    int rc = check_sim(sim, false);
+    if (rc) return rc;
+    if (!d_q || !d_actions || num_cols < 1 || num_cols > 127 || player < -1 || player > 1) return fail(EVG_E_ARG, "evg_decode_dqn: bad argument");
+    cudaError_t e = evg::launch_decode_dqn(d_q, num_cols, player, d_actions, sim->n_envs, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_decode_dqn_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
+int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t mod, int32_t player, int8_t* d_actions, void* stream)
+{
+    int rc = check_sim(sim, false);
+    if (rc) return rc;
+    if (!d_idx || !d_actions || div < 1 || mod < 1 || player < -1 || player > 1) return fail(EVG_E_ARG, "evg_decode_indices: bad argument");
+    cudaError_t e = evg::launch_decode_indices(d_idx, div, mod, player, d_actions, sim->n_envs, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_decode_indices_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
 int64_t evg_launch_count(const EvgSim* sim) { return sim ? sim->launches : -1; }
 
 }  // extern "C"

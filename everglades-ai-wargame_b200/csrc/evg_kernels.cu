@@ -751,6 +751,63 @@ __global__ void evg_agents_kernel(const __grid_constant__ Tables T, const uint32
 }
 
 // ---------------------------------------------------------------------------------------------
+// Policy-in-the-loop glue: network outputs -> int8 action rows, on the device.
+// evg_decode_dqn_kernel restates DQNAgent.filter_actions (agents/DQN/DQNAgent.py:161-197) exactly: a greedy
+// insertion over (node, group) in node-major order into 7 slots whose best-Q start at 0 and whose group ids start
+// at 0; a group already placed in another slot may only improve its own slot; the node written is the 0-based
+// column (the reference's off-by-one).  One thread per (match, player); q is [rows][12 * num_cols] float32.
+// ---------------------------------------------------------------------------------------------
+__global__ void evg_decode_dqn_kernel(const float* q, int num_cols, int player, int8_t* actions, int64_t n_envs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int np_ = player < 0 ? 2 : 1;
+    if (i >= n_envs * np_) return;
+    const int64_t env = i / np_;
+    const int p = player < 0 ? (int)(i % np_) : player;
+    const float* qi = q + i * (EVG_NUM_GROUPS * num_cols);
+    float bq[EVG_MAX_ACTIONS];
+    int bu[EVG_MAX_ACTIONS], bn[EVG_MAX_ACTIONS];
+#pragma unroll
+    for (int s = 0; s < EVG_MAX_ACTIONS; ++s) { bq[s] = 0.f; bu[s] = 0; bn[s] = 0; }
+    for (int n = 0; n < num_cols; ++n)
+        for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
+            const float v = qi[g * num_cols + n];
+            bool placed = false;
+#pragma unroll
+            for (int s = 0; s < EVG_MAX_ACTIONS; ++s) {
+                if (!placed && v > bq[s]) {
+                    bool in_units = false;  // `group_index in best_action_units`
+#pragma unroll
+                    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) in_units |= bu[k] == g;
+                    if (!(in_units && bu[s] != g)) {
+                        bq[s] = v; bu[s] = g; bn[s] = n;
+                        placed = true;
+                    }
+                }
+            }
+        }
+    uint16_t* out = reinterpret_cast<uint16_t*>(actions + (env * 2 + p) * (EVG_MAX_ACTIONS * 2));
+#pragma unroll
+    for (int s = 0; s < EVG_MAX_ACTIONS; ++s) out[s] = (uint16_t)((uint32_t)bu[s] | (uint32_t)bn[s] << 8);
+}
+
+// PPOAgent.get_action's unravel (agents/PPO/PPOAgent.py:122-127): units = idx // 12, nodes = idx % 11 (sic).
+__global__ void evg_decode_indices_kernel(const int64_t* idx, int div, int mod, int player, int8_t* actions, int64_t n_envs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int np_ = player < 0 ? 2 : 1;
+    if (i >= n_envs * np_ * EVG_MAX_ACTIONS) return;
+    const int64_t row = i / EVG_MAX_ACTIONS;
+    const int k = (int)(i % EVG_MAX_ACTIONS);
+    const int64_t env = row / np_;
+    const int p = player < 0 ? (int)(row % np_) : player;
+    const int64_t v = idx[i];
+    int8_t* out = actions + ((env * 2 + p) * EVG_MAX_ACTIONS + k) * 2;
+    out[0] = (int8_t)(v / div);
+    out[1] = (int8_t)(v % mod);
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 // DemoMap's node count gets a compile-time instantiation; any other map runs the generic one.
@@ -806,6 +863,22 @@ cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t
     const int64_t n = n_envs * (player < 0 ? 2 : 1);
     if (n <= 0) return cudaSuccess;
     evg_agent_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(t, records, actions, player, n_envs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_dqn(const float* q, int num_cols, int player, int8_t* actions, int64_t n_envs, cudaStream_t stream)
+{
+    const int64_t n = n_envs * (player < 0 ? 2 : 1);
+    if (n <= 0) return cudaSuccess;
+    evg_decode_dqn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(q, num_cols, player, actions, n_envs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_indices(const int64_t* idx, int div, int mod, int player, int8_t* actions, int64_t n_envs, cudaStream_t stream)
+{
+    const int64_t n = n_envs * (player < 0 ? 2 : 1) * EVG_MAX_ACTIONS;
+    if (n <= 0) return cudaSuccess;
+    evg_decode_indices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx, div, mod, player, actions, n_envs);
     return cudaGetLastError();
 }
 

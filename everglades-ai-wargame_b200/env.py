@@ -221,6 +221,32 @@ class BatchedEvergladesEnv:
         _capi.check(self._lib.evg_agents(self._h, int(agent0), int(agent1), C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ policy-in-the-loop glue
+    def decode_dqn(self, q, player=-1, out=None):
+        """Q-values float32 [N,2,12*C] (player=-1) or [N,12*C] -> action rows, exactly like DQNAgent.filter_actions
+        (agents/DQN/DQNAgent.py:161-197).  The policy forward itself is the caller's torch module on `self.obs`."""
+        torch = _torch()
+        out = self._actions if out is None else out
+        q = q.to(self.device, torch.float32).contiguous()
+        rows = self.num_envs * (2 if player < 0 else 1)
+        if q.numel() % (rows * _capi.NUM_GROUPS):
+            raise ValueError("q must hold 12*C values per (match, player)")
+        cols = q.numel() // (rows * _capi.NUM_GROUPS)
+        _capi.check(self._lib.evg_decode_dqn(self._h, C.c_void_p(q.data_ptr()), cols, int(player), C.c_void_p(out.data_ptr()),
+                                             self._stream()))
+        return out
+
+    def decode_indices(self, idx, div=12, mod=11, player=-1, out=None):
+        """Flat action indices int64 [N,2,7] (or [N,7]) -> rows (idx // div, idx % mod); defaults are PPOAgent.get_action's
+        (agents/PPO/PPOAgent.py:122-127)."""
+        torch = _torch()
+        out = self._actions if out is None else out
+        idx = idx.to(self.device, torch.int64).contiguous()
+        assert idx.numel() == self.num_envs * (2 if player < 0 else 1) * _capi.MAX_ACTIONS
+        _capi.check(self._lib.evg_decode_indices(self._h, C.c_void_p(idx.data_ptr()), int(div), int(mod), int(player),
+                                                 C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ snapshots
     def get_state(self, first=0, count=None):
         """numpy structured array (dtype _capi.env_state_dtype()) of matches [first, first+count)."""

@@ -226,6 +226,16 @@ int evg_agent_random(EvgSim* sim, int8_t* d_actions, int32_t player, void* strea
  * reference's agent objects); evg_reset(sim, NULL, ...) makes all of them fresh agents again. */
 int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_actions, void* stream);
 
+/* Policy-in-the-loop glue: decode network outputs into action rows on the device (player: 0, 1, or -1 = both;
+ * inputs are then [n_envs][2][...], else [n_envs][...]).
+ *   evg_decode_dqn:     float32 Q-values [..][12 * num_cols] -> rows, exactly as DQNAgent.filter_actions does
+ *                       (agents/DQN/DQNAgent.py:161-197; greedy insertion, node = 0-based column index).
+ *   evg_decode_indices: int64 flat indices [..][7] -> rows (idx / div, idx % mod); PPOAgent.get_action uses
+ *                       div 12, mod 11 (agents/PPO/PPOAgent.py:122-127), DQN's replay encoding div 11, mod 11. */
+int evg_decode_dqn(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int8_t* d_actions, void* stream);
+int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t mod, int32_t player, int8_t* d_actions,
+                       void* stream);
+
 /* Number of kernels this library has launched since creation (bench.py's gpu_launches). */
 int64_t evg_launch_count(const EvgSim* sim);
 
