@@ -35,6 +35,10 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+#ifndef EVG_DEFAULT_PAIR
+#define EVG_DEFAULT_PAIR false
+#endif
+
 struct EvgSim {
     EvgConfig cfg;
     evg::Tables tables;
@@ -47,9 +51,12 @@ struct EvgSim {
     int64_t launches;
     int64_t steps;
     EvgLayout layout;
-    bool use_tpm;     // thread-per-match step kernel (default) or the warp-per-match one (EVG_STEP_KERNEL=warp)
+    bool use_tpm;     // a row-based step kernel (tpm / pair) or the warp-per-match one (EVG_STEP_KERNEL=warp)
+    bool use_pair;    // two lanes per match (EVG_STEP_KERNEL=pair) instead of one thread per match (=tpm)
     size_t tpm_smem;
     int tpm_grid;  // persistent CTAs: SMs x resident CTAs
+    size_t pair_smem;
+    int pair_grid;
 };
 
 namespace {
@@ -284,6 +291,10 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     s->smem = (size_t)t.sm_tables_bytes + 128 + (size_t)evg::kWarpsPerBlock * t.sm_warp_stride;
     const char* which = getenv("EVG_STEP_KERNEL");
     s->use_tpm = !(which && strcmp(which, "warp") == 0);
+    s->use_pair = which ? strcmp(which, "pair") == 0 : EVG_DEFAULT_PAIR;
+    int pair_per_sm = 0;
+    if ((e = evg::pair_prepare(t, &s->pair_smem, &pair_per_sm)) != cudaSuccess || pair_per_sm < 1) { delete s; return cuda_fail(e, "lane-pair kernel setup"); }
+    s->pair_grid = prop.multiProcessorCount * pair_per_sm;
     int tpm_per_sm = 0;
     if ((e = evg::tpm_prepare(t, &s->tpm_smem, &tpm_per_sm)) != cudaSuccess || tpm_per_sm < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
     s->tpm_grid = prop.multiProcessorCount * tpm_per_sm;
@@ -392,8 +403,9 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.status = d_status;
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
-    cudaError_t e = sim->use_tpm ? evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream)
-                                 : evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream);
+    cudaError_t e = !sim->use_tpm  ? evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream)
+                    : sim->use_pair ? evg::launch_step_pair(sim->tables, a, sim->pair_smem, sim->pair_grid, (cudaStream_t)stream)
+                                    : evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;
     sim->steps += 1;

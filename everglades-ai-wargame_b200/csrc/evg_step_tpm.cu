@@ -24,106 +24,11 @@
 //
 // Reference semantics are cited per phase (server.py / env.py as in evg_kernels.cu); the checker is
 // oracle/evg_oracle.c.
-#include "evg_internal.h"
+#include "evg_step_common.cuh"
 
 namespace evg {
 
 namespace {
-
-template <int NODES>
-struct Geo {
-    const Tables& S;
-    __device__ __forceinline__ explicit Geo(const Tables& s) : S(s) {}
-    __device__ __forceinline__ int n_nodes() const { return NODES ? NODES : S.n_nodes; }
-    __device__ __forceinline__ int nn() const { return n_nodes() + 1; }
-    __device__ __forceinline__ int obs_len() const { return 1 + 4 * n_nodes() + 5 * EVG_NUM_GROUPS; }
-    __device__ __forceinline__ int rw() const { return NODES ? ((kRecNode0 + NODES) * 4 + 31) / 32 * 8 : S.rec_words8 * 2; }
-};
-
-// numpy's pairwise float64 sum (np.sum at server.py:481) over hv[0..size), size <= MAXSZ <= 16.
-template <int MAXSZ>
-__device__ __forceinline__ double np_sum_regs(const double (&hv)[MAXSZ], int size)
-{
-    if (MAXSZ < 8 || size < 8) {  // n < 8: left to right from 0.0
-        double res = 0.0;
-#pragma unroll
-        for (int i = 0; i < (MAXSZ < 7 ? MAXSZ : 7); ++i)
-            if (i < size) res = __dadd_rn(res, hv[i]);
-        return res;
-    }
-    double r[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        r[k] = hv[k];
-        if (MAXSZ == 16 && size == 16) r[k] = __dadd_rn(hv[k], hv[8 + k]);  // one more block of 8
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-#pragma unroll
-    for (int i = 8; i < (MAXSZ < 15 ? MAXSZ : 15); ++i)
-        if (i < size && size < 16) res = __dadd_rn(res, hv[i]);  // remainder, sequential
-    return res;
-}
-
-// Read a group's health row (issued early so that DRAM latency overlaps the draws).  Groups start on
-// 32-byte sectors and are padded to 4 slots, so 16-byte pairs never leave the row.
-template <int MAXSZ>
-__device__ __forceinline__ void load_group(const double* __restrict__ hp, int size, double (&hv)[MAXSZ])
-{
-#pragma unroll
-    for (int u = 0; u < MAXSZ; u += 2) {
-        double2 t = make_double2(0.0, 0.0);
-        if (u < size) t = __ldcs(reinterpret_cast<const double2*>(hp + u));
-        hv[u] = t.x;
-        hv[u + 1] = t.y;
-    }
-}
-
-// One target group: apply the damage histogram to its units, write hit units back.  Returns the new
-// alive mask and the observation's avg health (server.py:573-643, :480-491).
-template <int MAXSZ, typename HistT>
-__device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
-                                                const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
-                                                int* avg_out)
-{
-    // pass 1: damage aimed at every alive unit.  infliction[uid]: uid -> r-th unit alive before combat
-    uint32_t dv[MAXSZ];
-    int rank = 0;
-    uint32_t dmax = 0;
-#pragma unroll
-    for (int u = 0; u < MAXSZ; ++u) {
-        const bool on = u < size && ((alive0 >> u) & 1u);
-        dv[u] = on ? (uint32_t)hist[tb + rank] : 0u;
-        rank += on ? 1 : 0;
-        dmax = max(dmax, dv[u]);
-    }
-    // pass 2: loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601, from the
-    // table of those same fp64 quotients; all lookups are independent and issued together (ltab[0] == 0.0)
-    double loss[MAXSZ];
-#pragma unroll
-    for (int u = 0; u < MAXSZ; ++u) loss[u] = __ldg(ltab + min(dv[u], (uint32_t)(kLossD - 1)));
-    if (dmax >= (uint32_t)kLossD) {  // damage sums beyond the table: the division itself
-#pragma unroll
-        for (int u = 0; u < MAXSZ; ++u)
-            if (dv[u] >= (uint32_t)kLossD) loss[u] = __ddiv_rn(__dmul_rn(10.0, (double)dv[u]), divisor);
-    }
-    uint32_t alive = alive0;
-#pragma unroll
-    for (int u = 0; u < MAXSZ; ++u) {
-        if (dv[u]) {
-            double h = __dsub_rn(hv[u], loss[u]);  // server.py:609
-            if (h <= 0.0) {                        // server.py:615-618
-                h = 0.0;
-                alive &= ~(1u << u);
-            }
-            hv[u] = h;
-            hp[u] = h;
-        }
-    }
-    const double hsum = np_sum_regs<MAXSZ>(hv, size);
-    *avg_out = alive ? (int)__ddiv_rn(hsum, (double)__popc(alive)) : 0;  // int((health*1.)/units_alive), :491
-    return alive;
-}
 
 // game_init state (server.py:133-209) for one match: record row in shared memory + health refill
 __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* health, int n_nodes)
@@ -135,23 +40,6 @@ __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* hea
     for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
     double2* hp = reinterpret_cast<double2*>(health);
     for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
-}
-
-// k-th (0-based) set bit of a 24-bit mask
-__device__ __forceinline__ int kth_set_bit(uint32_t mask, int k)
-{
-    int pos = 0;
-    int t = __popc(mask & 0xFFFu);
-    if (k >= t) { pos = 12; k -= t; mask >>= 12; }
-    t = __popc(mask & 0x3Fu);
-    if (k >= t) { pos += 6; k -= t; mask >>= 6; }
-    t = __popc(mask & 0x7u);
-    if (k >= t) { pos += 3; k -= t; mask >>= 3; }
-    t = mask & 1u;
-    if (k >= t) { pos += 1; k -= t; mask >>= 1; }
-    t = mask & 1u;
-    if (k >= t) pos += 1;
-    return pos;
 }
 
 template <int NODES, int MAXSZ, typename HistT, int PITCH>

@@ -30,8 +30,10 @@ def write_configs(tmp_path, budget, turn_limit=60, bonus=300):
     return str(tmp_path)
 
 
+@pytest.mark.parametrize("kernel", ["pair", "tpm"])
 @pytest.mark.parametrize("budget", [60, 100, 120, 180, 192, 12])
-def test_other_map_units_and_budgets(tmp_path, budget):
+def test_other_map_units_and_budgets(tmp_path, budget, kernel, monkeypatch):
+    monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
     import __graft_entry__ as g
     g.build()
     import evgsim

@@ -252,11 +252,19 @@ def test_step_host_equals_step(evg, eo, cfg):
     assert env.h2d_bytes_per_step() == n * 28 and env.d2h_bytes_per_step() == n * (840 + 8 + 1)
 
 
-def test_warp_per_match_kernel_still_matches_oracle(evg, eo, cfg, monkeypatch):
-    """The earlier warp-per-match step kernel stays selectable (EVG_STEP_KERNEL=warp) for A/B profiling."""
-    monkeypatch.setenv("EVG_STEP_KERNEL", "warp")
+@pytest.mark.parametrize("kernel", ["pair", "tpm", "warp"])
+def test_every_step_kernel_matches_oracle(evg, eo, cfg, monkeypatch, kernel):
+    """The three step kernels (two lanes per match / one thread per match / one warp per match) stay selectable
+    (EVG_STEP_KERNEL) for A/B profiling; each must match the oracle, with auto-reset and a tail batch (n % 128 != 0)."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
     rng = np.random.default_rng(31)
-    run_against_oracle(evg, eo, cfg, 1024, 150, seed=19, first=7, make_actions=lambda s: adjacent_actions(rng, s, cfg))
+    cfg.turn_limit = 70
+    try:
+        run_against_oracle(evg, eo, cfg, 1000, 160, seed=19, first=7, make_actions=lambda s: adjacent_actions(rng, s, cfg),
+                           auto_reset=2)
+    finally:
+        cfg.turn_limit = 150
+        cfg.auto_reset = 0
 
 
 def test_fused_agents_equal_agent_kernel_plus_step(evg, eo, cfg):
