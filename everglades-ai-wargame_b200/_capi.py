@@ -20,6 +20,7 @@ ABI_VERSION = 1
 
 AUTORESET_OFF, AUTORESET_TERMINAL, AUTORESET_NEXT = 0, 1, 2
 STATUS_IN_PROGRESS, STATUS_TIME_EXPIRED, STATUS_BASE_CAPTURE, STATUS_ANNIHILATION = 0, 1, 2, 3
+SHAPE_NORMALIZED_SCORE, SHAPE_BASIC, SHAPE_PENALIZE_LONG, SHAPE_SHORT_GAMES = 0, 1, 2, 3
 AGENT_EXTERNAL, AGENT_RANDOM, AGENT_BASE_RUSH, AGENT_SWARM = 0, 1, 2, 3
 BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_AGENTS, BIND_COUNT = 0, 1, 2, 3, 4, 5
 
@@ -155,6 +156,7 @@ SYMBOLS = [
     ("evg_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_decode_dqn", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_decode_indices", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    ("evg_shape_reward", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     ("evg_launch_count", C.c_int64, [_P]),
     ("evg_last_error", C.c_char_p, []),
     ("evg_abi_version", C.c_int, []),

@@ -567,6 +567,19 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
     return EVG_OK;
 }
 
+int evg_shape_reward(EvgSim* sim, int32_t mode, const float* d_reward, const uint8_t* d_done, const float* d_obs, float* d_out,
+                     void* stream)
+{
+    int rc = check_sim(sim, false);
+    if (rc) return rc;
+    if (!d_reward || !d_done || !d_obs || !d_out || mode < EVG_SHAPE_NORMALIZED_SCORE || mode > EVG_SHAPE_SHORT_GAMES)
+        return fail(EVG_E_ARG, "evg_shape_reward: bad argument");
+    cudaError_t e = evg::launch_shape_reward(mode, d_reward, d_done, d_obs, sim->layout.obs_len, d_out, sim->n_envs, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_shape_reward_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
 int64_t evg_launch_count(const EvgSim* sim) { return sim ? sim->launches : -1; }
 
 }  // extern "C"

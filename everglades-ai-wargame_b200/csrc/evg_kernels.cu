@@ -807,6 +807,28 @@ __global__ void evg_decode_indices_kernel(const int64_t* idx, int div, int mod, 
     out[1] = (int8_t)(v % mod);
 }
 
+// Reward shaping of the training scripts (utils/reward_shaping.py:17-56), one thread per (match, player).
+// turnNum there is the number of steps played BEFORE this one = current_turn - 1, read from the observation.
+__global__ void evg_shape_reward_kernel(int mode, const float* reward, const uint8_t* done, const float* obs, int obs_len,
+                                        float* out, int64_t n_envs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_envs * 2) return;
+    const int64_t env = i >> 1;
+    const int p = (int)(i & 1);
+    const float mine = reward[env * 2 + p], other = reward[env * 2 + 1 - p];
+    const bool d = done[env] != 0, win = mine > other;
+    const float turn_num = obs[env * 2 * obs_len] - 1.f;
+    float r;
+    switch (mode) {
+        case EVG_SHAPE_BASIC: r = (d && win) ? 1.f : 0.f; break;                                     // basic_reward, :29-37
+        case EVG_SHAPE_PENALIZE_LONG: r = d ? (win ? 100.f : -0.1f) : -0.001f; break;                // penalize_long_games, :17-27
+        case EVG_SHAPE_SHORT_GAMES: r = d ? (win ? (float)((150.0 - (double)turn_num) / 150.0) : -1.f) : 0.f; break;  // :39-50
+        default: r = mine; break;                                                                    // normalized_score, :52-57
+    }
+    out[i] = r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -879,6 +901,14 @@ cudaError_t launch_decode_indices(const int64_t* idx, int div, int mod, int play
     const int64_t n = n_envs * (player < 0 ? 2 : 1) * EVG_MAX_ACTIONS;
     if (n <= 0) return cudaSuccess;
     evg_decode_indices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx, div, mod, player, actions, n_envs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shape_reward(int mode, const float* reward, const uint8_t* done, const float* obs, int obs_len, float* out,
+                                int64_t n_envs, cudaStream_t stream)
+{
+    if (n_envs <= 0) return cudaSuccess;
+    evg_shape_reward_kernel<<<(unsigned)((n_envs * 2 + 255) / 256), 256, 0, stream>>>(mode, reward, done, obs, obs_len, out, n_envs);
     return cudaGetLastError();
 }
 

@@ -247,6 +247,18 @@ class BatchedEvergladesEnv:
                                                  C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    def shape_reward(self, mode, out=None):
+        """utils/reward_shaping.py on the device: mode = _capi.SHAPE_* ; returns float32 [N,2] from the last step's
+        reward/done/obs tensors (turnNum = observed turn - 1)."""
+        torch = _torch()
+        if out is None:
+            if getattr(self, "_shaped", None) is None:
+                self._shaped = torch.empty((self.num_envs, 2), dtype=torch.float32, device=self.device)
+            out = self._shaped
+        _capi.check(self._lib.evg_shape_reward(self._h, int(mode), C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                               C.c_void_p(self.obs.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ snapshots
     def get_state(self, first=0, count=None):
         """numpy structured array (dtype _capi.env_state_dtype()) of matches [first, first+count)."""

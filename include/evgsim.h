@@ -236,6 +236,16 @@ int evg_decode_dqn(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t play
 int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t mod, int32_t player, int8_t* d_actions,
                        void* stream);
 
+/* Reward shaping of the reference's training scripts (utils/reward_shaping.py:17-56) on the step's outputs:
+ * d_out float32 [n_envs][2].  turnNum (steps played before this one) is read from the observation's turn
+ * field, so use it with EVG_AUTORESET_OFF or _TERMINAL (the observation of a finished match is the terminal one). */
+#define EVG_SHAPE_NORMALIZED_SCORE 0
+#define EVG_SHAPE_BASIC 1
+#define EVG_SHAPE_PENALIZE_LONG 2
+#define EVG_SHAPE_SHORT_GAMES 3
+int evg_shape_reward(EvgSim* sim, int32_t mode, const float* d_reward, const uint8_t* d_done, const float* d_obs, float* d_out,
+                     void* stream);
+
 /* Number of kernels this library has launched since creation (bench.py's gpu_launches). */
 int64_t evg_launch_count(const EvgSim* sim);
 

@@ -32,3 +32,16 @@ def dqn_filter_actions(q, num_groups=12, num_nodes=11, n_actions=7):
 def ppo_unravel(idx, div=12, mod=11):
     idx = np.asarray(idx).astype(np.int64)
     return np.stack([idx // div, idx % mod], axis=-1)
+
+
+def shape_reward(mode, player, reward, done, turn_num):
+    """utils/reward_shaping.py:17-56 restated: mode 0 normalized_score, 1 basic_reward, 2 penalize_long_games,
+    3 reward_short_games."""
+    mine, other = reward[player], reward[1 - player]
+    if mode == 1:
+        return 1.0 if (done and mine > other) else 0.0
+    if mode == 2:
+        return (100.0 if mine > other else -0.1) if done else -0.001
+    if mode == 3:
+        return ((150.0 - turn_num) / 150.0 if mine > other else -1.0) if done else 0.0
+    return mine

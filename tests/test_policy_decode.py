@@ -45,3 +45,39 @@ def test_device_decode_matches_reference():
         want = np.stack([pd.dqn_filter_actions(v) for v in qv.cpu().numpy().reshape(-1, 132)]).reshape(n, 2, 7, 2)
         assert np.array_equal(a.cpu().numpy(), want)
         obs, _, _, _ = env.step(a)
+
+
+def test_reward_shaping_restatement_matches_reference_functions():
+    import importlib.util
+    path = "/root/reference/utils/reward_shaping.py"
+    if not os.path.isfile(path):
+        pytest.skip("reference checkout not present")
+    spec = importlib.util.spec_from_file_location("ref_reward_shaping", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    fns = {0: ref.normalized_score, 1: ref.basic_reward, 2: ref.penalize_long_games, 3: ref.reward_short_games}
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        rew = {0: float(rng.choice([0, 1, -1, 0.3, 0.31])), 1: float(rng.choice([0, 1, -1, 0.3, 0.29]))}
+        done, turn = bool(rng.integers(2)), int(rng.integers(0, 150))
+        for mode, fn in fns.items():
+            for p in (0, 1):
+                assert pd.shape_reward(mode, p, rew, done, turn) == fn(p, rew, done, turn)
+
+
+@pytest.mark.gpu
+def test_device_reward_shaping():
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+    cfg = evgsim.load_config(turn_limit=30, auto_reset=1)
+    n = 256
+    env = evgsim.BatchedEvergladesEnv(n, seed=3, config=cfg, auto_reset=1)
+    env.reset()
+    for t in range(65):
+        obs, rew, done, _ = env.step_agents()
+        o, r, d = obs.cpu().numpy(), rew.cpu().numpy().astype(np.float64), done.cpu().numpy()
+        for mode in range(4):
+            got = env.shape_reward(mode).cpu().numpy()
+            want = np.array([[pd.shape_reward(mode, p, r[i], bool(d[i]), float(o[i, 0, 0]) - 1.0) for p in range(2)] for i in range(n)])
+            assert np.array_equal(got, want.astype(np.float32)), (t, mode)
