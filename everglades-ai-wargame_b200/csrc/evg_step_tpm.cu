@@ -24,6 +24,8 @@
 //
 // Reference semantics are cited per phase (server.py / env.py as in evg_kernels.cu); the checker is
 // oracle/evg_oracle.c.
+#include <cstdlib>
+
 #include "evg_step_common.cuh"
 
 namespace evg {
@@ -525,7 +527,8 @@ Variant pick(const Tables& t)
 
 cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
 {
-    const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kTpmThreads * t.tpm_pitch * 4;
+    size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kTpmThreads * t.tpm_pitch * 4;
+    if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
     cudaError_t e;
 
