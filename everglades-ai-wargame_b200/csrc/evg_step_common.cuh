@@ -40,21 +40,30 @@ __device__ __forceinline__ double np_sum_regs(const double (&hv)[MAXSZ], int siz
     return res;
 }
 
+// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): a 64-byte health row of 8 units is two requests
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d)
+{
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // Read a group's health row (issued early so that DRAM latency overlaps the draws).  Groups start on
-// 32-byte sectors and are padded to 4 slots, so 16-byte pairs never leave the row.
+// 32-byte sectors and are padded to 4 slots, so 32-byte quads never leave the row.
 template <int MAXSZ>
 __device__ __forceinline__ void load_group(const double* __restrict__ hp, int size, double (&hv)[MAXSZ])
 {
+    static_assert(MAXSZ % 4 == 0, "rows are read in quads of units");
 #pragma unroll
-    for (int u = 0; u < MAXSZ; u += 2) {
-        double2 t = make_double2(0.0, 0.0);
-        if (u < size) t = __ldcs(reinterpret_cast<const double2*>(hp + u));
-        hv[u] = t.x;
-        hv[u + 1] = t.y;
+    for (int u = 0; u < MAXSZ; u += 4) {
+        hv[u] = hv[u + 1] = hv[u + 2] = hv[u + 3] = 0.0;
+        if (u < size) ldg256(hp + u, hv[u], hv[u + 1], hv[u + 2], hv[u + 3]);
     }
 }
 
-// One target group: apply the damage histogram to its units, write hit units back.  Returns the new
+// One target group: apply the damage histogram to its units, write the touched quads back.  Returns the new
 // alive mask and the observation's avg health (server.py:573-643, :480-491).
 template <int MAXSZ, typename HistT>
 __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
@@ -92,9 +101,11 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
                 alive &= ~(1u << u);
             }
             hv[u] = h;
-            hp[u] = h;
         }
     }
+#pragma unroll
+    for (int u = 0; u < MAXSZ; u += 4)  // one 32-byte store per quad that was hit (padding slots keep what was read)
+        if (dv[u] | dv[u + 1] | dv[u + 2] | dv[u + 3]) stg256(hp + u, hv[u], hv[u + 1], hv[u + 2], hv[u + 3]);
     const double hsum = np_sum_regs<MAXSZ>(hv, size);
     *avg_out = alive ? (int)__ddiv_rn(hsum, (double)__popc(alive)) : 0;  // int((health*1.)/units_alive), :491
     return alive;
