@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
     // table of those same fp64 quotients; all lookups are independent and issued together (ltab[0] == 0.0)
     double loss[MAXSZ];
 #pragma unroll
-    for (int u = 0; u < MAXSZ; ++u) loss[u] = __ldg(ltab + min(dv[u], (uint32_t)(kLossD - 1)));
+    for (int u = 0; u < MAXSZ; ++u) loss[u] = dv[u] ? __ldg(ltab + min(dv[u], (uint32_t)(kLossD - 1))) : 0.0;  // no request for unhit units
     if (dmax >= (uint32_t)kLossD) {  // damage sums beyond the table: the division itself
 #pragma unroll
         for (int u = 0; u < MAXSZ; ++u)
