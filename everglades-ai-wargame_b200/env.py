@@ -190,10 +190,15 @@ class BatchedEvergladesEnv:
             raise RuntimeError("call reset() before step()")
         torch = _torch()
         hb = self.host_buffers()
+        src = hb["actions"]
         if actions is not None:
-            hb["actions"].copy_(torch.as_tensor(actions).to(torch.int8).reshape(hb["actions"].shape))
+            if isinstance(actions, torch.Tensor) and actions.dtype == torch.int8 and actions.device.type == "cpu" \
+                    and actions.is_pinned() and actions.is_contiguous() and tuple(actions.shape) == tuple(src.shape):
+                src = actions  # already page-locked: DMA straight from the caller's buffer
+            else:
+                src.copy_(torch.as_tensor(actions).to(torch.int8).reshape(src.shape))
         _capi.check(self._lib.evg_step_host(
-            self._h, C.c_void_p(hb["actions"].data_ptr()), C.c_void_p(hb["obs"].data_ptr()),
+            self._h, C.c_void_p(src.data_ptr()), C.c_void_p(hb["obs"].data_ptr()),
             C.c_void_p(hb["reward"].data_ptr()), C.c_void_p(hb["done"].data_ptr()),
             C.c_void_p(self._actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
             C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), self._stream()))
