@@ -61,3 +61,54 @@ def test_other_map_units_and_budgets(tmp_path, budget, kernel, monkeypatch):
             assert_states_equal(env.get_state(), ora.states, "turn %d" % (t + 1))
     assert deaths > 0  # the scenario really fights
     assert env.episode_stats()["episodes"] >= 2 * n
+
+
+def write_ring32(tmp_path):
+    """The largest supported map: 32 nodes on a ring with chords, bases at 1 and 17, mirror map i -> ((i + 15) % 32) + 1."""
+    n = 32
+    nodes = []
+    for i in range(1, n + 1):
+        nb = {(i % n) + 1: 2 + i % 3, ((i - 2) % n) + 1: 2 + (i - 1) % 3, ((i + 7) % n) + 1: 5, ((i - 9) % n) + 1: 5}
+        nodes.append({"ID": i, "Connections": [{"ConnectedID": d, "Distance": w} for d, w in sorted(nb.items())],
+                      "ControlPoints": 300 if i in (1, 17) else 50 + i, "Resource": ["DEFEND"] if i % 5 == 0 else (["OBSERVE"] if i % 7 == 0 else []),
+                      "StructureDefense": 1 + (i % 4) * 0.25, "TeamStart": {1: 0, 17: 1}.get(i, -1)})
+    p1 = [0] + [((i + 15) % n) + 1 for i in range(1, n + 1)]
+    (tmp_path / "Ring32.json").write_text(json.dumps({"MapName": "ring32", "nodes": nodes, "P1NodeMap": p1}))
+    (tmp_path / "Setup.json").write_text(json.dumps({"TurnLimit": 50, "CaptureBonus": 700, "UnitBudget": 100}))
+    return str(tmp_path)
+
+
+@pytest.mark.parametrize("kernel", ["tpm", "pair", "warp"])
+def test_largest_map_32_nodes(tmp_path, kernel, monkeypatch):
+    """32 nodes: 352-byte records (more than one 8-byte word per lane), 189-value observations, the byte-array
+    variant of the random agent, run-time-sized kernels."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+    from oracle import evg_oracle as eo
+
+    d = write_ring32(tmp_path)
+    cfg = evgsim.load_config(d, "Ring32.json", evgsim.DEFAULT_CONFIG_DIR + "/UnitDefinitions.json", "Setup.json", auto_reset=1)
+    n = 300
+    env = evgsim.BatchedEvergladesEnv(n, seed=8, config=cfg, auto_reset=1, env_id_offset=40)
+    ora = eo.OracleBatch(cfg, n, seed=8, first=40)
+    assert env.obs_len == 1 + 4 * 32 + 60 and env.layout.record_bytes == 352
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
+    rng = np.random.default_rng(3)
+    for t in range(120):
+        if t % 4 == 3:  # the on-device random agent on a map too large for its register-only variant
+            acts = env.random_actions().cpu().numpy()
+            for i in range(0, n, 37):
+                for p in range(2):
+                    want = eo.agent_random(cfg, 8, 40 + i, int(ora.states[i]["episode"]), int(ora.states[i]["turn"]) + 1, p)
+                    assert np.array_equal(acts[i, p], want.astype(np.int8))
+        else:
+            acts = adjacent_actions(rng, ora.states, cfg)
+        obs, rew, done, info = env.step(acts)
+        oobs, orew, odone = ora.step(acts)
+        assert np.array_equal(done.cpu().numpy(), odone), t
+        assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+        assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
+    assert_states_equal(env.get_state(), ora.states, "end")
+    assert env.episode_stats()["episodes"] >= 2 * n
