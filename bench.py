@@ -138,7 +138,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
