@@ -134,7 +134,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    """The in-tree library; EVGSIM_LIB names another build of the same sources (kernel A/B runs, tools/ab_variants.sh)."""
+    return os.environ.get("EVGSIM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 # every symbol include/evgsim.h declares: (name, restype, argtypes)
@@ -157,6 +158,7 @@ SYMBOLS = [
     ("evg_decode_dqn", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_decode_indices", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     ("evg_shape_reward", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
+    ("evg_step_kernel_kind", C.c_int, [_P]),
     ("evg_launch_count", C.c_int64, [_P]),
     ("evg_last_error", C.c_char_p, []),
     ("evg_abi_version", C.c_int, []),

@@ -155,8 +155,11 @@ class BatchedEvergladesEnv:
         aptr = None
         if ext:
             aptr = C.c_void_p(self._as_actions(actions).data_ptr())
-        elif want_actions or not {int(agent0), int(agent1)} <= {_capi.AGENT_EXTERNAL, _capi.AGENT_RANDOM}:
-            aptr = C.c_void_p(self._actions.data_ptr())  # observation-driven agents run as their own kernel
+        elif (want_actions or not {int(agent0), int(agent1)} <= {_capi.AGENT_EXTERNAL, _capi.AGENT_RANDOM}
+              or self._lib.evg_step_kernel_kind(self._h) == 0):
+            # observation-driven agents, and any agent next to the warp-per-match kernel (small batches), run as
+            # their own kernel and hand their rows over in the action buffer
+            aptr = C.c_void_p(self._actions.data_ptr())
         _capi.check(self._lib.evg_step_agents(self._h, int(agent0), int(agent1), aptr, C.c_void_p(self.obs.data_ptr()),
                                               C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
                                               C.c_void_p(self.status.data_ptr()), C.c_void_p(self.scores.data_ptr()),

@@ -246,6 +246,11 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
 int evg_shape_reward(EvgSim* sim, int32_t mode, const float* d_reward, const uint8_t* d_done, const float* d_obs, float* d_out,
                      void* stream);
 
+/* Which step kernel evg_create() selected: 0 = a warp per match (small batches), 1 = a thread per match,
+ * 2 = a lane pair per match.  Scripted agents are fused into kernels 1 and 2 only; with
+ * kernel 0 evg_step_agents() needs a non-NULL d_actions to pass the generated rows through.  -1 if sim is NULL. */
+int evg_step_kernel_kind(const EvgSim* sim);
+
 /* Number of kernels this library has launched since creation (bench.py's gpu_launches). */
 int64_t evg_launch_count(const EvgSim* sim);
 
