@@ -182,15 +182,22 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.sm_misc = t.sm_obs + round_up(2 * t.obs_len * 4, 16);
     t.sm_warp_stride = t.sm_misc + 528 + n_big * 16 * 8;
     t.sm_tables_bytes = round_up((int)sizeof(evg::Tables), 16);
-    // thread-per-match kernel: per-thread row = record + scratch; u8 histograms when no target can collect > 255 damage
+    // u8 damage histograms when no target can collect > 255 damage in a turn
     t.tpm_hist16 = max_dmg_sum > 255 ? 1 : 0;
-    t.tpm_hwords = (max_units * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
-    {
-        const int scr_combat = 2 * nn + 2 * t.tpm_hwords, scr_post = 2 * nn + 32;
+    {   // lane-pair kernel: per-thread row = padded record + scratch with per-match histograms
+        t.pair_hwords = (max_units * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
+        const int scr_combat = 2 * nn + 2 * t.pair_hwords, scr_post = 2 * nn + 32;
         int pitch = t.rec_words8 * 2 + (scr_combat > scr_post ? scr_combat : scr_post);
         pitch += pitch & 1;
         if (((pitch / 2) & 1) == 0) pitch += 2;  // pitch/2 odd: conflict-free 4- and 8-byte column accesses
+        t.pair_pitch = pitch;
+    }
+    {   // thread-per-match kernel: per-thread row = the record's used words + 2 words per node + the observation
+        // staging window; the damage histograms of one round (<= 32 fighting groups) live in a per-warp pool
+        int pitch = round_up(evg::kRecNode0 + c.n_nodes, 2) + 2 * nn + evg::kTpmStage;
+        if (((pitch / 2) & 1) == 0) pitch += 2;
         t.tpm_pitch = pitch;
+        t.tpm_pool_words = (32 * round_up(max_size, 4) * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
     }
     *out = t;
     return EVG_OK;

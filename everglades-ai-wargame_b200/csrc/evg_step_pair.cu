@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) evg_step_pair_kernel(const __
 
     const Geo<NODES> G(S);
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
-    const int P = PITCH ? PITCH : T.tpm_pitch;
+    const int P = PITCH ? PITCH : T.pair_pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pm = lane >> 1, sd = lane & 1;  // my match within the warp, my side
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes + 128);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) evg_step_pair_kernel(const __
                 base += t;
             }
         }
-        uint32_t* H = X + 2 * nn + sd * S.tpm_hwords;  // targets on my side
+        uint32_t* H = X + 2 * nn + sd * S.pair_hwords;  // targets on my side
         for (int i = 0; i < (int)((base * sizeof(HistT) + 3) / 4); ++i) H[i] = 0;
         const char* he = reinterpret_cast<const char*>(A.health + env * S.health_slots);
         for (uint32_t m = fm; m; m &= m - 1) {  // start my fighting groups' health rows towards L2
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) evg_step_pair_kernel(const __
                 // draws, :549-566; 8 draws of 16 bits per Philox block (oracle/tape.py)
                 const uint32_t dmg = S.g_damage[L];
                 const uint32_t turn_m = Rm[kRecTurn] + 1u, ep_m = Rm[kRecEpisode];
-                uint32_t* hw = Xm + 2 * nn + (1 - side) * S.tpm_hwords;
+                uint32_t* hw = Xm + 2 * nn + (1 - side) * S.pair_hwords;
                 for (int b = 0; 8 * b < cnt; ++b) {
                     uint32_t r[4];
                     philox4x32_10(S.env_base + (uint32_t)(warp_env0 + m), turn_m,
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) evg_step_pair_kernel(const __
                 const int type = S.g_type[L];
                 const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
-                const HistT* hist = reinterpret_cast<const HistT*>(Xm + 2 * nn + side * S.tpm_hwords);
+                const HistT* hist = reinterpret_cast<const HistT*>(Xm + 2 * nn + side * S.pair_hwords);
                 int avg;
                 const uint32_t alive = apply_group<MAXSZ, HistT>(hp, hv, S.g_size[L], w1 & 0xFFFFu, hist, tb, ltab, divisor, &avg);
                 Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
@@ -482,7 +482,7 @@ enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
 
 Variant pick(const Tables& t)
 {
-    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == 138) return V_FAST;
+    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.pair_pitch == 138) return V_FAST;
     return t.tpm_hist16 ? V_GENERIC16 : V_GENERIC8;
 }
 
@@ -490,7 +490,7 @@ Variant pick(const Tables& t)
 
 cudaError_t pair_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
 {
-    const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kPairMatches * t.tpm_pitch * 4;
+    const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kPairMatches * t.pair_pitch * 4;
     *smem_out = smem;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<11, 12, uint8_t, 138>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;

@@ -18,9 +18,12 @@
 //     out by the warp as contiguous float2 runs (two matches per store instruction);
 //   * unit health is read as whole 64/96-byte group rows (full 32-byte sectors), only for groups that
 //     fight, and only hit units are written back.
-// Scratch per thread (dynamic indexing needs addressable storage): node member masks, two damage
-// histograms, capture accumulators.  IEEE fp64 health arithmetic as in the reference; the per-hit
-// division is a lookup in a host-built table of the SAME fp64 quotients for damage sums < 32.
+// Scratch per thread (dynamic indexing needs addressable storage): two words per node (member masks and unit
+// totals in combat, capture accumulators afterwards) and the observation staging window.  The damage
+// histograms of a combat round live in a per-WARP pool (a round is <= 32 fighting groups, so <= 32 x 12
+// entries), which keeps the row at 102 words and lets 4 CTAs (16 warps) share an SM.  IEEE fp64 health
+// arithmetic as in the reference; the per-hit division is a lookup in a host-built table of the SAME fp64
+// quotients for damage sums < 32.
 //
 // Reference semantics are cited per phase (server.py / env.py as in evg_kernels.cu); the checker is
 // oracle/evg_oracle.c.
@@ -45,7 +48,7 @@ __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* hea
 }
 
 template <int NODES, int MAXSZ, typename HistT, int PITCH>
-__global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
+__global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     // ---- stage the static tables once per CTA
@@ -61,10 +64,12 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
     const int P = PITCH ? PITCH : T.tpm_pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes + 128);
+    const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes);
     uint32_t* wrow = rows + (size_t)warp * 32 * P;  // the warp's 32 rows
     uint32_t* R = wrow + (size_t)lane * P;          // my record
-    uint32_t* X = R + RW;                           // my scratch
+    uint32_t* X = R + RWU;                          // my scratch
+    uint32_t* pool = rows + (size_t)(kTpmThreads / 32) * 32 * P + (size_t)warp * T.tpm_pool_words;  // the warp's histogram pool
     // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
     // touches its own 32 rows, so batches need no CTA-wide barrier
     const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
@@ -100,8 +105,8 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
             const uint4 v = __ldcs(g4 + f);
             uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
-            d[0] = make_uint2(v.x, v.y);
-            d[1] = make_uint2(v.z, v.w);
+            if (NODES || 4 * q < RWU) d[0] = make_uint2(v.x, v.y);
+            if (4 * q + 2 < RWU) d[1] = make_uint2(v.z, v.w);  // the record's padding words are not kept
         }
     }
     __syncwarp();
@@ -169,30 +174,35 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
 
     // ---- combat, server.py:503-654
     {
-        // per-thread preparation, scratch layout (words): X[0..nn) member masks of the groups present at
-        // each node, X[nn..2nn) per-node totals and histogram bases, X[2nn..) two damage histograms
-        uint32_t fm = 0;  // my match's fighting groups
+        // per-thread preparation.  Scratch (words): X[x] for player 0 and X[nn + x] for player 1 hold, per node,
+        // member mask of the groups present [0:12) | their alive units [16:24) | histogram base of that side [24:32)
+        uint32_t fm = 0;          // my match's fighting groups (bit L = side * 12 + gid)
+        uint32_t b0 = 0, b1 = 0;  // histogram entries per side = alive units of the fighting groups
         if (valid) {
-            for (int i = 0; i < nn; ++i) X[i] = 0;
+            for (int i = 0; i < nn; ++i) reinterpret_cast<uint2*>(X)[i] = make_uint2(0u, 0u);
+            {
+                uint32_t* __restrict__ acc0 = X;
+                uint32_t* __restrict__ acc1 = X + nn;
 #pragma unroll 4
-            for (int L = 0; L < kGroupLanes; ++L) {  // listed and not in transit, :516-535
-                const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);
-                if ((w.y & 0xFFFFu) && !(w.x & W0_MOVING)) X[w.x & W0_LOC_MASK] |= 1u << L;
+                for (int g = 0; g < EVG_NUM_GROUPS; ++g) {  // listed and not in transit, :516-535; entry 0 takes the rest
+                    const uint2 wa = *reinterpret_cast<const uint2*>(R + 2 * g);
+                    const uint2 wb = *reinterpret_cast<const uint2*>(R + 2 * (EVG_NUM_GROUPS + g));
+                    const uint32_t aa = wa.y & 0xFFFFu, ab = wb.y & 0xFFFFu;
+                    const bool pa = aa && !(wa.x & W0_MOVING), pb = ab && !(wb.x & W0_MOVING);
+                    const uint32_t la = pa ? wa.x & W0_LOC_MASK : 0u, lb = pb ? wb.x & W0_LOC_MASK : 0u;
+                    const uint32_t va = acc0[la], vb = acc1[lb];
+                    acc0[la] = va + (1u << g | (uint32_t)__popc(aa) << 16);
+                    acc1[lb] = vb + (1u << g | (uint32_t)__popc(ab) << 16);
+                }
             }
-            uint32_t b0 = 0, b1 = 0;
             for (int x = 1; x <= n_nodes; ++x) {
-                const uint32_t mem = X[x];
-                if ((mem & 0xFFFu) && (mem >> EVG_NUM_GROUPS)) {  // both players present: contested, :539
-                    fm |= mem;
-                    uint32_t t0 = 0, t1 = 0;  // np.sum(counts[pid]), :552-553
-                    for (uint32_t m = mem; m; m &= m - 1) {
-                        const int L = __ffs(m) - 1;
-                        const uint32_t c = __popc(R[2 * L + 1] & 0xFFFFu);
-                        if (L >= EVG_NUM_GROUPS) t1 += c; else t0 += c;
-                    }
-                    X[nn + x] = t0 | t1 << 8 | b0 << 16 | b1 << 24;  // node-local uid -> histogram slot base
-                    b0 += t0;
-                    b1 += t1;
+                const uint32_t a = X[x], b = X[nn + x];
+                if ((a & 0xFFFu) && (b & 0xFFFu)) {  // both players present: contested, :539
+                    fm |= (a & 0xFFFu) | (b & 0xFFFu) << EVG_NUM_GROUPS;
+                    X[x] = a | b0 << 24;  // np.sum(counts[pid]) at [16:24) (:552-553), node-local uid -> histogram entry base
+                    X[nn + x] = b | b1 << 24;
+                    b0 += a >> 16;
+                    b1 += b >> 16;
                 }
             }
             // the health rows of the groups that will fight: start them towards L2 now
@@ -205,27 +215,31 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                     if (S.g_size[L] > 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + 64));
                 }
             }
-            uint32_t* H = X + 2 * nn;
-            for (int i = 0; i < (int)((b0 * sizeof(HistT) + 3) / 4); ++i) H[i] = 0;
-            for (int i = 0; i < (int)((b1 * sizeof(HistT) + 3) / 4); ++i) H[S.tpm_hwords + i] = 0;
         }
-        __syncwarp();  // rows (actions applied, masks, zeroed histograms) are read by other lanes from here on
+        __syncwarp();  // rows (actions applied, node words) are read by other lanes from here on
         // the warp's work list = concatenation of the matches' fighting groups; a round takes whole
-        // matches (a match has <= 24 items), so draws and apply of one match stay in one round
+        // matches (a match has <= 24 items), so draws and apply of one match stay in one round and the
+        // round's histograms fit the warp's pool: match m owns entries [upre[m] - upre[m_begin], +b0+b1)
         const int nitems = __popc(fm);
         int incl = nitems;
+        uint32_t uincl = b0 + b1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += t;
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, uincl, o);
+            if (lane >= o) { incl += t; uincl += u; }
         }
         const int pre = incl - nitems;
+        const uint32_t ub = (uincl - (b0 + b1)) | b0 << 16;  // entries before my match [0:16) | my side-0 entries [16:24)
         const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         int m_begin = 0;
         while (total && m_begin < 32) {
             const int base = __shfl_sync(0xFFFFFFFFu, pre, m_begin);
             const int m_end = __popc(__ballot_sync(0xFFFFFFFFu, incl - base <= 32));
             const int nround = __shfl_sync(0xFFFFFFFFu, incl, m_end - 1) - base;
+            const uint32_t ubase = __shfl_sync(0xFFFFFFFFu, ub, m_begin) & 0xFFFFu;
+            const uint32_t uround = __shfl_sync(0xFFFFFFFFu, uincl, m_end - 1) - ubase;
+            for (uint32_t i = lane; i < (uround * (uint32_t)sizeof(HistT) + 3u) / 4u; i += 32) pool[i] = 0;
             const int q = base + lane;
             int m = 0;  // largest m with pre[m] <= q
 #pragma unroll
@@ -236,14 +250,16 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             }
             const int pm = __shfl_sync(0xFFFFFFFFu, pre, m);
             const uint32_t fmm = __shfl_sync(0xFFFFFFFFu, fm, m);
+            const uint32_t ubm = __shfl_sync(0xFFFFFFFFu, ub, m);
             const bool act = lane < nround;
             // item state kept across the two phases
             uint32_t* Rm = wrow + (size_t)m * P;
-            uint32_t* Xm = Rm + RW;
+            uint32_t* Xm = Rm + RWU;
             int L = 0, side = 0, x = 1, tb = 0;
             uint32_t w0 = 0, w1 = 0;
             double hv[MAXSZ];
             double* hp = A.health;
+            __syncwarp();  // pool zeroed
             if (act) {
                 L = kth_set_bit(fmm, q - pm);
                 hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
@@ -254,14 +270,15 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                 w1 = Rm[2 * L + 1];
                 x = (int)(w0 & W0_LOC_MASK);
                 const int cnt = __popc(w1 & 0xFFFFu);
-                const uint32_t info = Xm[nn + x];
-                const uint32_t n = side ? info & 0xFFu : (info >> 8) & 0xFFu;       // opposing units at the node
-                const uint32_t hb = side ? (info >> 16) & 0xFFu : info >> 24;       // opposing histogram base
-                tb = (int)(side ? info >> 24 : (info >> 16) & 0xFFu);               // my side's base at this node
+                const uint32_t own = Xm[side * nn + x], opp = Xm[(1 - side) * nn + x];
+                const uint32_t n = (opp >> 16) & 0xFFu;                        // opposing units at the node
+                const uint32_t mb = (ubm & 0xFFFFu) - ubase, mb0 = ubm >> 16;  // my match's pool entries; its side-0 count
+                const uint32_t hb = mb + (side ? 0u : mb0) + (opp >> 24);      // opposing histogram base at this node
+                tb = (int)(mb + (side ? mb0 : 0u) + (own >> 24));              // my side's base at this node
                 // my group's range starts after the groups listed before it (arrival order, then gid:
                 // node.groups[pid], :198,690-691); sibling counts are still pre-combat here
                 const uint32_t key = (w1 >> 16) << 4 | (uint32_t)gg;
-                for (uint32_t sm = (side ? Xm[x] >> EVG_NUM_GROUPS : Xm[x] & 0xFFFu) & ~(1u << gg); sm; sm &= sm - 1) {
+                for (uint32_t sm = (own & 0xFFFu) & ~(1u << gg); sm; sm &= sm - 1) {
                     const int g = __ffs(sm) - 1;
                     const uint32_t w1g = Rm[2 * (side * EVG_NUM_GROUPS + g) + 1];
                     if (((w1g >> 16) << 4 | (uint32_t)g) < key) tb += __popc(w1g & 0xFFFFu);
@@ -270,7 +287,6 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                 // its type's damage to infliction[uid]; 8 draws of 16 bits per Philox block (oracle/tape.py)
                 const uint32_t dmg = S.g_damage[L];
                 const uint32_t turn_m = Rm[kRecTurn] + 1u, ep_m = Rm[kRecEpisode];
-                uint32_t* hw = Xm + 2 * nn + (1 - side) * S.tpm_hwords;
                 for (int b = 0; 8 * b < cnt; ++b) {
                     uint32_t r[4];
                     philox4x32_10(S.env_base + (uint32_t)(warp_env0 + m), turn_m,
@@ -280,8 +296,8 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                         if (8 * b + k < cnt) {
                             const uint32_t half = (k & 1) ? r[k >> 1] >> 16 : r[k >> 1] & 0xFFFFu;
                             const uint32_t idx = hb + ((half * n) >> 16);
-                            if (sizeof(HistT) == 1) atomicAdd(&hw[idx >> 2], dmg << ((idx & 3u) * 8));
-                            else atomicAdd(&hw[idx >> 1], dmg << ((idx & 1u) * 16));
+                            if (sizeof(HistT) == 1) atomicAdd(&pool[idx >> 2], dmg << ((idx & 3u) * 8));
+                            else atomicAdd(&pool[idx >> 1], dmg << ((idx & 1u) * 16));
                         }
                 }
             }
@@ -294,9 +310,9 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
                 const int type = S.g_type[L];
                 const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
-                const HistT* hist = reinterpret_cast<const HistT*>(Xm + 2 * nn + side * S.tpm_hwords);
                 int avg;
-                const uint32_t alive = apply_group<MAXSZ, HistT>(hp, hv, S.g_size[L], w1 & 0xFFFFu, hist, tb, ltab, divisor, &avg);
+                const uint32_t alive = apply_group<MAXSZ, HistT>(hp, hv, S.g_size[L], w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool), tb,
+                                                                 ltab, divisor, &avg);
                 Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
                 Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
             }
@@ -432,11 +448,13 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
     }
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
-    // Each thread packs 32 floats at a time into the staging window of its row; the warp streams the
-    // windows out as contiguous float2 runs (2 matches x 128 B per store instruction).
+    // Each thread packs kTpmStage floats at a time into the staging window of its row; the warp streams the
+    // windows out as contiguous float2 runs (64 / kTpmStage matches x 4 * kTpmStage bytes per store instruction).
     {
-        float2* stage = reinterpret_cast<float2*>(X + 2 * nn);  // rows, RW and 2*nn are even: 8-byte aligned
-        const int stage_off = RW + 2 * nn;
+        constexpr int SP = kTpmStage / 2;   // float2 per window
+        constexpr int MPI = 32 / SP;        // matches per store instruction
+        float2* stage = reinterpret_cast<float2*>(X + 2 * nn);  // rows, RWU and 2*nn are even: 8-byte aligned
+        const int stage_off = RWU + 2 * nn;
         const int npairs = OL;  // 2*OL floats per match = OL float2
         float* obs_base = A.obs + warp_env0 * 2 * OL;
         auto value = [&](int f) -> float {  // f = index into the match's 2*OL floats
@@ -459,26 +477,26 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
             if (j == 3) return (float)((w0 >> 21) & 1u);
             return (float)__popc(R[2 * L + 1] & 0xFFFFu);
         };
-        const int half = lane >> 4, c16 = lane & 15;
-        const int nchunks = (npairs + 15) / 16;
+        const int sub = lane / SP, cp = lane % SP;
+        const int nchunks = (npairs + SP - 1) / SP;
 #pragma unroll
-        for (int c = 0; c < (NODES ? (1 + 4 * NODES + 60 + 15) / 16 : nchunks); ++c) {
+        for (int c = 0; c < (NODES ? (1 + 4 * NODES + 60 + SP - 1) / SP : nchunks); ++c) {
             if (valid) {
-                float vals[32];  // all reads first (they can be merged and overlapped), then the staging stores
+                float vals[2 * SP];  // all reads first (they can be merged and overlapped), then the staging stores
 #pragma unroll
-                for (int k = 0; k < 32; ++k) vals[k] = 32 * c + k < 2 * npairs ? value(32 * c + k) : 0.f;
+                for (int k = 0; k < 2 * SP; ++k) vals[k] = 2 * SP * c + k < 2 * npairs ? value(2 * SP * c + k) : 0.f;
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (16 * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
+                for (int k = 0; k < SP; ++k)
+                    if (SP * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
             }
             __syncwarp();
-            const int pr = 16 * c + c16;
+            const int pr = SP * c + cp;
             if (pr < npairs) {
 #pragma unroll
-                for (int it = 0; it < 16; ++it) {
-                    const int m = 2 * it + half;
+                for (int it = 0; it < 32 / MPI; ++it) {
+                    const int m = MPI * it + sub;
                     if (m < nvalid) {
-                        const float2 v = *reinterpret_cast<const float2*>(wrow + (size_t)m * P + stage_off + 2 * c16);
+                        const float2 v = *reinterpret_cast<const float2*>(wrow + (size_t)m * P + stage_off + 2 * cp);
                         __stcs(reinterpret_cast<float2*>(obs_base + (size_t)m * 2 * OL) + pr, v);
                     }
                 }
@@ -497,16 +515,21 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
     }
     __syncwarp();
 
-    // ---- cooperative, coalesced store of the records
+    // ---- cooperative, coalesced store of the records (the padding words are written as zeros)
     {
         const int q4 = RW / 4;
         uint4* g4 = reinterpret_cast<uint4*>(A.records) + warp_env0 * q4;
         const int total = nvalid * q4;
+        const int used = kRecNode0 + n_nodes;
 #pragma unroll 4
         for (int f = lane; f < total; f += 32) {
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
-            const uint2* s = reinterpret_cast<const uint2*>(wrow + (size_t)m * P + 4 * q);
-            const uint2 a = s[0], b = s[1];
+            const uint32_t* sw = wrow + (size_t)m * P + 4 * q;
+            uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+            if (NODES || 4 * q < RWU) a = *reinterpret_cast<const uint2*>(sw);
+            if (4 * q + 2 < RWU) b = *reinterpret_cast<const uint2*>(sw + 2);
+            if (4 * q + 1 >= used) a.y = 0u;
+            if (4 * q + 3 >= used) b.y = 0u;
             g4[f] = make_uint4(a.x, a.y, b.x, b.y);
         }
     }
@@ -514,12 +537,15 @@ __global__ void __launch_bounds__(kTpmThreads) evg_step_tpm_kernel(const __grid_
     }  // batch loop
 }
 
+// DemoMap row: 62 record words + 24 node words + the staging window, pitch / 2 odd
+constexpr int kFastPitch = (((62 + 24 + kTpmStage) / 2) & 1) ? 62 + 24 + kTpmStage : 62 + 24 + kTpmStage + 2;
+
 // which instantiation serves this config
 enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
 
 Variant pick(const Tables& t)
 {
-    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == 138) return V_FAST;
+    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == kFastPitch) return V_FAST;
     return t.tpm_hist16 ? V_GENERIC16 : V_GENERIC8;
 }
 
@@ -527,16 +553,16 @@ Variant pick(const Tables& t)
 
 cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
 {
-    size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kTpmThreads * t.tpm_pitch * 4;
+    size_t smem = (size_t)t.sm_tables_bytes + (size_t)kTpmThreads * t.tpm_pitch * 4 + (size_t)(kTpmThreads / 32) * t.tpm_pool_words * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
     cudaError_t e;
 
-    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, 138>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     switch (pick(t)) {
-        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, 138>, kTpmThreads, smem); break;
+        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch>, kTpmThreads, smem); break;
         case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint8_t, 0>, kTpmThreads, smem); break;
         default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint16_t, 0>, kTpmThreads, smem); break;
     }
@@ -549,7 +575,7 @@ cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, int
     const int64_t nb = (a.n_envs + kTpmThreads - 1) / kTpmThreads;
     const unsigned grid = (unsigned)(nb < max_grid ? nb : max_grid);
     switch (pick(t)) {
-        case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, 138><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
         case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
         default: evg_step_tpm_kernel<0, 16, uint16_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
     }
