@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             // all 14 rows are decoded and looked up first (independent shared-memory reads in flight together:
             // accepting a row changes neither the group's location nor its moving flag), then resolved in order
             int Lr[2 * EVG_MAX_ACTIONS];
-            uint32_t dr[2 * EVG_MAX_ACTIONS], nr[2 * EVG_MAX_ACTIONS];
+            uint32_t neww[2 * EVG_MAX_ACTIONS];
+            uint32_t okrows = 0;
 #pragma unroll
             for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) {
                 const uint32_t a = rows[r];
@@ -154,17 +155,17 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 const uint32_t gw0 = R[2 * L];
                 const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
                 Lr[r] = L;
-                nr[r] = (uint32_t)an;
-                dr[r] = (okg && !(gw0 & W0_MOVING)) ? d : 0u;  // t2 (not moving) and t3 (adjacent), :243-250
+                if (okg && !(gw0 & W0_MOVING) && d) okrows |= 1u << r;  // t2 (not moving) and t3 (adjacent), :243-250
+                neww[r] = (gw0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | (uint32_t)an << W0_DEST_SHIFT |
+                          d << W0_DIST_SHIFT | W0_READY;  // :267-270
             }
             uint32_t used = 0;
 #pragma unroll
             for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) {
-                if (dr[r] && !((used >> Lr[r]) & 1u)) {  // t1: the group has no accepted command yet, :241
+                const bool ok = ((okrows >> r) & 1u) && !((used >> Lr[r]) & 1u);  // t1: the group has no accepted command yet, :241
+                if (ok) {
                     used |= 1u << Lr[r];
-                    const uint32_t gw0 = R[2 * Lr[r]];
-                    R[2 * Lr[r]] = (gw0 & ~((0x3Fu << W0_DEST_SHIFT) | (0xFFu << W0_DIST_SHIFT))) | nr[r] << W0_DEST_SHIFT |
-                                   dr[r] << W0_DIST_SHIFT | W0_READY;  // :267-270
+                    R[2 * Lr[r]] = neww[r];
                 }
             }
         }
@@ -330,31 +331,28 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         {
             uint32_t* __restrict__ acc0 = X;
             uint32_t* __restrict__ acc1 = X + nn;
+            // written with selects: the four cases (idle, ready, under way, arriving) differ per match, so branches
+            // would run them one after the other
             auto move = [&](int L, uint32_t& v, uint32_t& loc, int& pts) {
                 const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);
-                uint32_t w0 = w.x;
-                const uint32_t alive = w.y & 0xFFFFu;
-                v = 0; loc = 0; pts = 0;
-                if (alive) {  // destroyed groups are skipped, :663
-                    if (w0 & W0_READY) {
-                        w0 = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
-                    } else if (w0 & W0_MOVING) {
-                        const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[L];  // :671
-                        if (dist <= 0) {  // arrived: appended to the destination's list (:678-695)
-                            w0 = (w0 & (127u << W0_AVG_SHIFT)) | ((w0 >> W0_DEST_SHIFT) & 0x3Fu);
-                            R[2 * L + 1] = alive | turn << 16;
-                        } else {
-                            w0 = (w0 & ~(0xFFu << W0_DIST_SHIFT)) | (uint32_t)dist << W0_DIST_SHIFT;
-                        }
-                    }
-                    R[2 * L] = w0;
-                    const uint32_t cnt = __popc(alive);
-                    v = cnt;
-                    if (!(w0 & W0_MOVING)) v |= (cnt * S.g_control[L]) << 10 | 1u << 24;
-                    loc = w0 & W0_LOC_MASK;
-                    pts = (int)cnt * (int)S.g_cost[L];
-                    any_alive = true;
-                }
+                const uint32_t w0 = w.x, alive = w.y & 0xFFFFu;
+                const bool live = alive != 0;  // destroyed groups are skipped, :663
+                const bool rdy = (w0 & W0_READY) != 0, mov = (w0 & W0_MOVING) != 0;
+                const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[L];  // :671
+                const bool arrive = live && !rdy && mov && dist <= 0;
+                const uint32_t w_rdy = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
+                const uint32_t w_arr = (w0 & (127u << W0_AVG_SHIFT)) | ((w0 >> W0_DEST_SHIFT) & 0x3Fu);  // appended to the destination's list (:678-695)
+                const uint32_t w_go = (w0 & ~(0xFFu << W0_DIST_SHIFT)) | ((uint32_t)dist & 0xFFu) << W0_DIST_SHIFT;
+                uint32_t n0 = rdy ? w_rdy : (mov ? (dist <= 0 ? w_arr : w_go) : w0);
+                n0 = live ? n0 : w0;
+                R[2 * L] = n0;
+                if (arrive) R[2 * L + 1] = alive | turn << 16;
+                const uint32_t cnt = __popc(alive);
+                const uint32_t hold = (n0 & W0_MOVING) ? 0u : ((cnt * S.g_control[L]) << 10 | 1u << 24);
+                v = live ? (cnt | hold) : 0u;
+                loc = live ? (n0 & W0_LOC_MASK) : 0u;
+                pts = (int)cnt * (int)S.g_cost[L];
+                any_alive |= live;
             };
 #pragma unroll 2
             for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
@@ -373,36 +371,32 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         // ---- capture (server.py:708-767; current_turn > 0 here) and node scoring (server.py:298-310)
         bool basecap = false;
         for (int n = 1; n <= n_nodes; ++n) {
-            uint32_t nw = R[kRecNode0 + n - 1];
+            const uint32_t nw = R[kRecNode0 + n - 1];
             int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
             const uint32_t a0 = X[n], a1 = X[nn + n];
             const bool c0 = (a0 >> 24) != 0, c1 = (a1 >> 24) != 0;
             const int cp = S.node_cp[n];
-            if (c0 != c1) {  // exactly one controller (:729)
-                const int pid = c1 ? 1 : 0;
-                if (abs(cs) < cp || pid != cb) {  // :731-732
-                    const int pts = (int)(((pid ? a1 : a0) >> 10) & 0x3FFFu), pxer = pid ? -1 : 1;
-                    const bool old_sign = cs < 0;  // :747-750, zero counts as player 0's sign
-                    cs += pts * pxer;
-                    const bool neutralize = old_sign != (cs < 0);
-                    if (abs(cs) >= cp) {  // :763-765
-                        cs = cp * pxer;
-                        cb = pid;
-                    }
-                    if (cb != -1 && neutralize) cb = -1;  // :766-767
-                    nw = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
-                    R[kRecNode0 + n - 1] = nw;
-                }
+            const int pid = c1 ? 1 : 0;
+            const bool upd = c0 != c1 && (abs(cs) < cp || pid != cb);  // exactly one controller (:729), :731-732
+            {
+                const int pts = (int)(((pid ? a1 : a0) >> 10) & 0x3FFFu), pxer = pid ? -1 : 1;
+                int cs2 = cs + pts * pxer;
+                const bool neutralize = (cs < 0) != (cs2 < 0);  // :747-750, zero counts as player 0's sign
+                const bool full = abs(cs2) >= cp;                 // :763-765
+                cs2 = full ? cp * pxer : cs2;
+                int cb2 = full ? pid : cb;
+                cb2 = neutralize ? -1 : cb2;  // :766-767
+                cs = upd ? cs2 : cs;
+                cb = upd ? cb2 : cb;
+                if (upd) R[kRecNode0 + n - 1] = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
             }
             const int ts = S.node_team_start[n];
-            if (ts != -1 && cb != -1 && cb != ts) {
-                basecap = true;
-                if (cb) s1 += S.capture_bonus; else s0 += S.capture_bonus;
-            }
-            if (cs != 0) {
-                const int pts = abs(cs) == cp ? 2 * cp : abs(cs);
-                if (cs > 0) s0 += pts; else s1 += pts;
-            }
+            const bool bc = ts != -1 && cb != -1 && cb != ts;
+            basecap |= bc;
+            const int bonus = bc ? S.capture_bonus : 0;
+            const int npts = abs(cs) == cp ? 2 * cp : abs(cs);
+            s0 += (cb ? 0 : bonus) + (cs > 0 ? npts : 0);
+            s1 += (cb ? bonus : 0) + (cs < 0 ? npts : 0);
         }
         if ((int)turn >= S.turn_limit) status = EVG_STATUS_TIME_EXPIRED;  // server.py:321-328, in that priority
         else if (!any_alive) status = EVG_STATUS_ANNIHILATION;
