@@ -73,40 +73,76 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
     // touches its own 32 rows, so batches need no CTA-wide barrier
     const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
+    const bool ext_rows = A.agent[0] == EVG_AGENT_EXTERNAL || A.agent[1] == EVG_AGENT_EXTERNAL;
+    // Software pipeline (compile-time map only: 16 chunks of 16 bytes per record): the NEXT batch's records and
+    // action rows are requested into registers before this batch's observation phase, so their DRAM latency is
+    // hidden behind a fifth of a batch's work instead of being exposed at the top of every batch
+    constexpr bool PIPE = NODES != 0 && EVG_TPM_PIPE != 0;
+    uint4 nxt[16];
+    uint32_t nxa[7];
+    bool have = false;
+    auto request = [&](int64_t b) -> bool {
+        const int64_t e0 = b * kTpmThreads + warp * 32;
+        if (b >= nbatches || e0 + 32 > A.n_envs) return false;  // partial warps take the direct path
+        const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + e0 * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nxt[i] = __ldcs(g4 + lane + 32 * i);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) nxa[k] = ext_rows ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + (e0 + lane) * 7 + k) : 0u;
+        return true;
+    };
+    if (PIPE) have = request(blockIdx.x);
     for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int64_t warp_env0 = batch * kTpmThreads + warp * 32;
     const int64_t env = warp_env0 + lane;
     const int64_t left = A.n_envs - warp_env0;
     const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
     const bool valid = lane < nvalid;
-    {   // pull the NEXT batch's records and action rows towards L2 while this one is processed
-        const int64_t nenv0 = warp_env0 + (int64_t)gridDim.x * kTpmThreads;
-        if (nenv0 + 32 <= A.n_envs) {
-            const char* nr = reinterpret_cast<const char*>(A.records) + nenv0 * RW * 4;
-            for (int b = lane * 128; b < 32 * RW * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + b));
-            const char* na = reinterpret_cast<const char*>(A.actions) + nenv0 * 28;
-            if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(na + lane * 128));
-        }
-    }
-
-    // this turn's action rows (7 words per match), requested before the records so the latencies overlap
-    uint32_t aw[7];
-    const bool ext_rows = A.agent[0] == EVG_AGENT_EXTERNAL || A.agent[1] == EVG_AGENT_EXTERNAL;
+    uint32_t aw[7];  // this turn's action rows (7 words per match)
+    if (PIPE && have) {
+        // ---- rows from the registers filled during the previous batch
 #pragma unroll
-    for (int k = 0; k < 7; ++k) aw[k] = (valid && ext_rows) ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
+        for (int k = 0; k < 7; ++k) aw[k] = nxa[k];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int f = lane + 32 * i, m = f >> 4, q = f & 15;
+            uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
+            d[0] = make_uint2(nxt[i].x, nxt[i].y);
+            if (4 * q + 2 < RWU) d[1] = make_uint2(nxt[i].z, nxt[i].w);  // the record's padding words are not kept
+        }
+    } else {
+        if (!PIPE) {  // pull the NEXT batch's records and action rows towards L2 while this one is processed
+            const int64_t nenv0 = warp_env0 + (int64_t)gridDim.x * kTpmThreads;
+            if (nenv0 + 32 <= A.n_envs) {
+                const char* nr = reinterpret_cast<const char*>(A.records) + nenv0 * RW * 4;
+                for (int b = lane * 128; b < 32 * RW * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + b));
+                const char* na = reinterpret_cast<const char*>(A.actions) + nenv0 * 28;
+                if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(na + lane * 128));
+            }
+        }
+        // action rows requested before the records so the latencies overlap
+#pragma unroll
+        for (int k = 0; k < 7; ++k) aw[k] = (valid && ext_rows) ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
 
-    // ---- cooperative, coalesced load of the warp's records into the per-thread rows
-    {
+        // ---- cooperative, coalesced load of the warp's records into the per-thread rows
         const int q4 = RW / 4;  // 16-byte chunks per record
         const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + warp_env0 * q4;
         const int total = nvalid * q4;
-#pragma unroll 8
-        for (int f = lane; f < total; f += 32) {
-            const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
-            const uint4 v = __ldcs(g4 + f);
-            uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
-            if (NODES || 4 * q < RWU) d[0] = make_uint2(v.x, v.y);
-            if (4 * q + 2 < RWU) d[1] = make_uint2(v.z, v.w);  // the record's padding words are not kept
+#pragma unroll 1
+        for (int f0 = 0; f0 < total; f0 += 32 * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = f0 + 32 * i + lane < total ? __ldcs(g4 + f0 + 32 * i + lane) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int f = f0 + 32 * i + lane;
+                if (f < total) {
+                    const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
+                    uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
+                    if (NODES || 4 * q < RWU) d[0] = make_uint2(v[i].x, v[i].y);
+                    if (4 * q + 2 < RWU) d[1] = make_uint2(v[i].z, v[i].w);
+                }
+            }
         }
     }
     __syncwarp();
@@ -441,6 +477,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         }
     }
 
+    if (PIPE) have = request(batch + gridDim.x);
+
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
     // Each thread packs kTpmStage floats at a time into the staging window of its row; the warp streams the
     // windows out as contiguous float2 runs (64 / kTpmStage matches x 4 * kTpmStage bytes per store instruction).
@@ -486,12 +524,20 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             __syncwarp();
             const int pr = SP * c + cp;
             if (pr < npairs) {
+                const uint32_t* srow = wrow + stage_off + 2 * cp;
+                float* orow = obs_base + 2 * pr;
+                if (nvalid == 32) {  // whole warp: no per-match predicates
 #pragma unroll
-                for (int it = 0; it < 32 / MPI; ++it) {
-                    const int m = MPI * it + sub;
-                    if (m < nvalid) {
-                        const float2 v = *reinterpret_cast<const float2*>(wrow + (size_t)m * P + stage_off + 2 * cp);
-                        __stcs(reinterpret_cast<float2*>(obs_base + (size_t)m * 2 * OL) + pr, v);
+                    for (int it = 0; it < 32 / MPI; ++it) {
+                        const int m = MPI * it + sub;
+                        const float2 v = *reinterpret_cast<const float2*>(srow + (size_t)m * P);
+                        __stcs(reinterpret_cast<float2*>(orow + (size_t)m * 2 * OL), v);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int m = sub; m < nvalid; m += MPI) {
+                        const float2 v = *reinterpret_cast<const float2*>(srow + (size_t)m * P);
+                        __stcs(reinterpret_cast<float2*>(orow + (size_t)m * 2 * OL), v);
                     }
                 }
             }
@@ -515,8 +561,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         uint4* g4 = reinterpret_cast<uint4*>(A.records) + warp_env0 * q4;
         const int total = nvalid * q4;
         const int used = kRecNode0 + n_nodes;
-#pragma unroll 4
-        for (int f = lane; f < total; f += 32) {
+        auto put = [&](int f) {
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
             const uint32_t* sw = wrow + (size_t)m * P + 4 * q;
             uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
@@ -525,6 +570,13 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             if (4 * q + 1 >= used) a.y = 0u;
             if (4 * q + 3 >= used) b.y = 0u;
             g4[f] = make_uint4(a.x, a.y, b.x, b.y);
+        };
+        if (NODES && nvalid == 32) {
+#pragma unroll
+            for (int i = 0; i < (NODES ? 16 : 1); ++i) put(lane + 32 * i);
+        } else {
+#pragma unroll 1
+            for (int f = lane; f < total; f += 32) put(f);
         }
     }
     __syncwarp();
