@@ -73,12 +73,18 @@ struct Tables {
 
 constexpr int kLossD = 32;
 constexpr int kAgentMaxNodes = 15;  // nibble-packed node permutation of the on-device random agent
-constexpr int kTpmThreads = 128;
+#ifndef EVG_TPM_THREADS
+#define EVG_TPM_THREADS 128
+#endif
+constexpr int kTpmThreads = EVG_TPM_THREADS;
 #ifndef EVG_TPM_STAGE
 #define EVG_TPM_STAGE 32
 #endif
 #ifndef EVG_TPM_MIN_CTAS
 #define EVG_TPM_MIN_CTAS 3
+#endif
+#ifndef EVG_TPM_SYNC
+#define EVG_TPM_SYNC 1  // the warps of a CTA pass the phases together (0: free-running, 1: all warps, 2: the warps of one scheduler)
 #endif
 #ifndef EVG_TPM_PIPE
 #define EVG_TPM_PIPE 1

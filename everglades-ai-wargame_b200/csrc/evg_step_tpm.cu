@@ -31,6 +31,20 @@
 
 #include "evg_step_common.cuh"
 
+#if EVG_TPM_SYNC == 1
+#define EVG_PHASE_SYNC() __syncthreads()
+#elif EVG_TPM_SYNC == 2
+#define EVG_PHASE_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kTpmThreads / 4) : "memory")
+#else
+#define EVG_PHASE_SYNC() ((void)0)
+#endif
+
+#ifdef EVG_TPM_SYNC_FINE
+#define EVG_PHASE_SYNC2() EVG_PHASE_SYNC()
+#else
+#define EVG_PHASE_SYNC2() ((void)0)
+#endif
+
 namespace evg {
 
 namespace {
@@ -146,6 +160,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         }
     }
     __syncwarp();
+    EVG_PHASE_SYNC();
 
     uint32_t turn = 0, episode = 0;
     int s0 = 0, s1 = 0, status = 0;
@@ -254,6 +269,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             }
         }
         __syncwarp();  // rows (actions applied, node words) are read by other lanes from here on
+        EVG_PHASE_SYNC();
         // the warp's work list = concatenation of the matches' fighting groups; a round takes whole
         // matches (a match has <= 24 items), so draws and apply of one match stay in one round and the
         // round's histograms fit the warp's pool: match m owns entries [upre[m] - upre[m_begin], +b0+b1)
@@ -358,6 +374,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         }
     }
 
+    EVG_PHASE_SYNC();
     if (valid) {
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
         //   [0:10) units of all listed groups (:446-449), [10:24) count*control of non-moving groups (:718-724),
@@ -478,6 +495,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }
 
     if (PIPE) have = request(batch + gridDim.x);
+    EVG_PHASE_SYNC();
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
     // Each thread packs kTpmStage floats at a time into the staging window of its row; the warp streams the
@@ -522,6 +540,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                     if (SP * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
             }
             __syncwarp();
+            EVG_PHASE_SYNC2();
             const int pr = SP * c + cp;
             if (pr < npairs) {
                 const uint32_t* srow = wrow + stage_off + 2 * cp;
@@ -555,6 +574,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }
     __syncwarp();
 
+    EVG_PHASE_SYNC();
     // ---- cooperative, coalesced store of the records (the padding words are written as zeros)
     {
         const int q4 = RW / 4;
