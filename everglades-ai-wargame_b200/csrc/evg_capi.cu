@@ -192,9 +192,10 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
         if (((pitch / 2) & 1) == 0) pitch += 2;  // pitch/2 odd: conflict-free 4- and 8-byte column accesses
         t.pair_pitch = pitch;
     }
-    {   // thread-per-match kernel: per-thread row = the record's used words + 2 words per node + the observation
-        // staging window; the damage histograms of one round (<= 32 fighting groups) live in a per-warp pool
-        int pitch = round_up(evg::kRecNode0 + c.n_nodes, 2) + 2 * nn + evg::kTpmStage;
+    {   // thread-per-match kernel: per-thread row = the record's used words + the observation staging window; two
+        // words per node and match are kept word-major per warp; the damage histograms of one round (<= 32
+        // fighting groups) live in a per-warp pool
+        int pitch = round_up(evg::kRecNode0 + c.n_nodes, 2) + evg::kTpmStage;
         if (((pitch / 2) & 1) == 0) pitch += 2;
         t.tpm_pitch = pitch;
         t.tpm_pool_words = (32 * round_up(max_size, 4) * (t.tpm_hist16 ? 2 : 1) + 3) / 4;

@@ -79,11 +79,14 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     const int P = PITCH ? PITCH : T.tpm_pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
-    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes);
-    uint32_t* wrow = rows + (size_t)warp * 32 * P;  // the warp's 32 rows
-    uint32_t* R = wrow + (size_t)lane * P;          // my record
-    uint32_t* X = R + RWU;                          // my scratch
-    uint32_t* pool = rows + (size_t)(kTpmThreads / 32) * 32 * P + (size_t)warp * T.tpm_pool_words;  // the warp's histogram pool
+    // per warp: 32 rows (record + observation staging window), the node words of its 32 matches stored
+    // word-major ([word][lane]: a thread's own accesses always hit bank `lane`, whatever the index), the pool
+    const int WS = 32 * P + 64 * nn + T.tpm_pool_words;
+    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes) + (size_t)warp * WS;  // the warp's 32 rows
+    uint32_t* R = wrow + (size_t)lane * P;  // my record
+    uint32_t* wx = wrow + 32 * P;           // node words of the warp's matches: word i of match m at wx[32 * i + m]
+    uint32_t* X = wx + lane;                // mine: X[32 * i]
+    uint32_t* pool = wx + 64 * nn;          // the warp's histogram pool
     // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
     // touches its own 32 rows, so batches need no CTA-wide barrier
     const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
@@ -226,15 +229,15 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
 
     // ---- combat, server.py:503-654
     {
-        // per-thread preparation.  Scratch (words): X[x] for player 0 and X[nn + x] for player 1 hold, per node,
+        // per-thread preparation.  Node words (word-major, X[32 * i]): i = x for player 0 and nn + x for player 1 hold, per node,
         // member mask of the groups present [0:12) | their alive units [16:24) | histogram base of that side [24:32)
         uint32_t fm = 0;          // my match's fighting groups (bit L = side * 12 + gid)
         uint32_t b0 = 0, b1 = 0;  // histogram entries per side = alive units of the fighting groups
         if (valid) {
-            for (int i = 0; i < nn; ++i) reinterpret_cast<uint2*>(X)[i] = make_uint2(0u, 0u);
+            for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
             {
                 uint32_t* __restrict__ acc0 = X;
-                uint32_t* __restrict__ acc1 = X + nn;
+                uint32_t* __restrict__ acc1 = X + 32 * nn;
 #pragma unroll 4
                 for (int g = 0; g < EVG_NUM_GROUPS; ++g) {  // listed and not in transit, :516-535; entry 0 takes the rest
                     const uint2 wa = *reinterpret_cast<const uint2*>(R + 2 * g);
@@ -242,17 +245,17 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                     const uint32_t aa = wa.y & 0xFFFFu, ab = wb.y & 0xFFFFu;
                     const bool pa = aa && !(wa.x & W0_MOVING), pb = ab && !(wb.x & W0_MOVING);
                     const uint32_t la = pa ? wa.x & W0_LOC_MASK : 0u, lb = pb ? wb.x & W0_LOC_MASK : 0u;
-                    const uint32_t va = acc0[la], vb = acc1[lb];
-                    acc0[la] = va + (1u << g | (uint32_t)__popc(aa) << 16);
-                    acc1[lb] = vb + (1u << g | (uint32_t)__popc(ab) << 16);
+                    const uint32_t va = acc0[32 * la], vb = acc1[32 * lb];
+                    acc0[32 * la] = va + (1u << g | (uint32_t)__popc(aa) << 16);
+                    acc1[32 * lb] = vb + (1u << g | (uint32_t)__popc(ab) << 16);
                 }
             }
             for (int x = 1; x <= n_nodes; ++x) {
-                const uint32_t a = X[x], b = X[nn + x];
+                const uint32_t a = X[32 * x], b = X[32 * (nn + x)];
                 if ((a & 0xFFFu) && (b & 0xFFFu)) {  // both players present: contested, :539
                     fm |= (a & 0xFFFu) | (b & 0xFFFu) << EVG_NUM_GROUPS;
-                    X[x] = a | b0 << 24;  // np.sum(counts[pid]) at [16:24) (:552-553), node-local uid -> histogram entry base
-                    X[nn + x] = b | b1 << 24;
+                    X[32 * x] = a | b0 << 24;  // np.sum(counts[pid]) at [16:24) (:552-553), node-local uid -> histogram entry base
+                    X[32 * (nn + x)] = b | b1 << 24;
                     b0 += a >> 16;
                     b1 += b >> 16;
                 }
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             const bool act = lane < nround;
             // item state kept across the two phases
             uint32_t* Rm = wrow + (size_t)m * P;
-            uint32_t* Xm = Rm + RWU;
+            const uint32_t* Xm = wx + m;
             int L = 0, side = 0, x = 1, tb = 0;
             uint32_t w0 = 0, w1 = 0;
             double hv[MAXSZ];
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 w1 = Rm[2 * L + 1];
                 x = (int)(w0 & W0_LOC_MASK);
                 const int cnt = __popc(w1 & 0xFFFFu);
-                const uint32_t own = Xm[side * nn + x], opp = Xm[(1 - side) * nn + x];
+                const uint32_t own = Xm[32 * (side * nn + x)], opp = Xm[32 * ((1 - side) * nn + x)];
                 const uint32_t n = (opp >> 16) & 0xFFu;                        // opposing units at the node
                 const uint32_t mb = (ubm & 0xFFFFu) - ubase, mb0 = ubm >> 16;  // my match's pool entries; its side-0 count
                 const uint32_t hb = mb + (side ? 0u : mb0) + (opp >> 24);      // opposing histogram base at this node
@@ -379,11 +382,11 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
         //   [0:10) units of all listed groups (:446-449), [10:24) count*control of non-moving groups (:718-724),
         //   [24:29) number of non-moving groups (:725-726); plus unit points for the score (:313-317)
-        for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
+        for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
         bool any_alive = false;
         {
             uint32_t* __restrict__ acc0 = X;
-            uint32_t* __restrict__ acc1 = X + nn;
+            uint32_t* __restrict__ acc1 = X + 32 * nn;
             // written with selects: the four cases (idle, ready, under way, arriving) differ per match, so branches
             // would run them one after the other
             auto move = [&](int L, uint32_t& v, uint32_t& loc, int& pts) {
@@ -413,9 +416,9 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 int pa, pb;
                 move(g, va, la, pa);
                 move(EVG_NUM_GROUPS + g, vb, lb, pb);
-                const uint32_t a = acc0[la], b = acc1[lb];  // entry 0 collects the (zero) contributions of dead groups
-                acc0[la] = a + va;
-                acc1[lb] = b + vb;
+                const uint32_t a = acc0[32 * la], b = acc1[32 * lb];  // entry 0 collects the (zero) contributions of dead groups
+                acc0[32 * la] = a + va;
+                acc1[32 * lb] = b + vb;
                 s0 += pa;
                 s1 += pb;
             }
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         for (int n = 1; n <= n_nodes; ++n) {
             const uint32_t nw = R[kRecNode0 + n - 1];
             int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
-            const uint32_t a0 = X[n], a1 = X[nn + n];
+            const uint32_t a0 = X[32 * n], a1 = X[32 * (nn + n)];
             const bool c0 = (a0 >> 24) != 0, c1 = (a1 >> 24) != 0;
             const int cp = S.node_cp[n];
             const int pid = c1 ? 1 : 0;
@@ -487,10 +490,10 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         reset_row(S, R, A.health + env * S.health_slots, n_nodes);
         turn = 0;
         episode += 1;
-        for (int i = 0; i < 2 * nn; ++i) X[i] = 0;
+        for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
         for (int L = 0; L < kGroupLanes; ++L) {
             const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
-            X[(L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK)] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;
+            X[32 * ((L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK))] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;
         }
     }
 
@@ -503,8 +506,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     {
         constexpr int SP = kTpmStage / 2;   // float2 per window
         constexpr int MPI = 32 / SP;        // matches per store instruction
-        float2* stage = reinterpret_cast<float2*>(X + 2 * nn);  // rows, RWU and 2*nn are even: 8-byte aligned
-        const int stage_off = RWU + 2 * nn;
+        float2* stage = reinterpret_cast<float2*>(R + RWU);  // P and RWU are even: 8-byte aligned
+        const int stage_off = RWU;
         const int npairs = OL;  // 2*OL floats per match = OL float2
         float* obs_base = A.obs + warp_env0 * 2 * OL;
         auto value = [&](int f) -> float {  // f = index into the match's 2*OL floats
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 if (j == 0) return (float)(S.node_flags[x] & 1u);
                 if (j == 1) return (float)((S.node_flags[x] >> 1) & 1u);
                 if (j == 2) return (float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu);  // raw sign for both viewers
-                return (float)(X[(p ? 0 : nn) + x] & 1023u);                                  // opposing listed units
+                return (float)(X[32 * ((p ? 0 : nn) + x)] & 1023u);                                  // opposing listed units
             }
             const int q = i - 1 - 4 * n_nodes, g = q / 5, j = q - 5 * g;
             const int L = p * EVG_NUM_GROUPS + g;
@@ -603,8 +606,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }  // batch loop
 }
 
-// DemoMap row: 62 record words + 24 node words + the staging window, pitch / 2 odd
-constexpr int kFastPitch = (((62 + 24 + kTpmStage) / 2) & 1) ? 62 + 24 + kTpmStage : 62 + 24 + kTpmStage + 2;
+// DemoMap row: 62 record words + the staging window, pitch / 2 odd
+constexpr int kFastPitch = (((62 + kTpmStage) / 2) & 1) ? 62 + kTpmStage : 62 + kTpmStage + 2;
 
 // which instantiation serves this config
 enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
@@ -619,7 +622,7 @@ Variant pick(const Tables& t)
 
 cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
 {
-    size_t smem = (size_t)t.sm_tables_bytes + (size_t)kTpmThreads * t.tpm_pitch * 4 + (size_t)(kTpmThreads / 32) * t.tpm_pool_words * 4;
+    size_t smem = (size_t)t.sm_tables_bytes + (size_t)(kTpmThreads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
     cudaError_t e;
