@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <new>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -124,6 +125,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
             t.g_type[L] = (uint8_t)type;
             t.g_size[L] = (uint8_t)size;
             t.g_big[L] = size > 8 ? (uint8_t)n_big++ : (uint8_t)0;
+            if (size > 8) t.big_mask |= 1u << L;
             t.g_damage[L] = t.ut_damage[type];
             t.g_speed[L] = t.ut_speed[type];
             t.g_control[L] = t.ut_control[type];
@@ -184,6 +186,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     t.sm_tables_bytes = round_up((int)sizeof(evg::Tables), 16);
     // u8 damage histograms when no target can collect > 255 damage in a turn
     t.tpm_hist16 = max_dmg_sum > 255 ? 1 : 0;
+    t.max_damage_sum = max_dmg_sum;
     {   // lane-pair kernel: per-thread row = padded record + scratch with per-match histograms
         t.pair_hwords = (max_units * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
         const int scr_combat = 2 * nn + 2 * t.pair_hwords, scr_post = 2 * nn + 32;
@@ -325,7 +328,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
     L.stats_bytes = evg::ST_COUNT * 8;
     L.agents_bytes = n_envs * 16;
-    L.tables_bytes = (int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * evg::kLossD * 8;
+    L.tables_bytes = (int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8;  // loss table, then reciprocals
     *out = s;
     return EVG_OK;
 }
@@ -358,21 +361,39 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
     {
         const EvgConfig& c = sim->cfg;
         const int nn = c.n_nodes + 1;
-        std::vector<double> tab((size_t)c.n_unit_types * nn * 3 * evg::kLossD, 0.0);
+        const size_t n_div = (size_t)c.n_unit_types * nn * 3;
+        std::vector<double> tab(n_div * (evg::kLossD + 1), 0.0);
+        // ... followed by the reciprocal of every divisor.  The kernel then forms the quotient without a division:
+        // q0 = a*r, q = fma(fma(-q0, D, a), r, q0) (Markstein's correction), used only if it reproduces a/D for
+        // EVERY reachable numerator a = 10*d of every divisor D, which is checked here exhaustively
+        bool fast = true;
         for (int t = 0; t < c.n_unit_types; ++t)
             for (int x = 1; x <= c.n_nodes; ++x)
                 for (int b = 0; b < 3; ++b) {
                     volatile double node_def = (double)b * c.node_defense[x];
                     volatile double divisor = c.unit_armor[t] + node_def;
+                    const size_t ti = (size_t)(t * nn + x) * 3 + b;
                     for (int d = 0; d < evg::kLossD; ++d) {
                         volatile double num = 10.0 * (double)d;
-                        tab[((size_t)(t * nn + x) * 3 + b) * evg::kLossD + d] = num / divisor;
+                        tab[ti * evg::kLossD + d] = num / divisor;
+                    }
+                    volatile double r = 1.0 / divisor;
+                    tab[n_div * evg::kLossD + ti] = r;
+                    for (int d = 1; d <= sim->tables.max_damage_sum && fast; ++d) {
+                        volatile double a = 10.0 * (double)d;
+                        volatile double q0 = a * r;
+                        volatile double rem = fma(-q0, divisor, a);
+                        volatile double q = fma(rem, r, q0);
+                        volatile double ref = a / divisor;
+                        if (!(q == ref)) fast = false;
                     }
                 }
         cudaError_t e = cudaSetDevice(sim->device);
         if (e == cudaSuccess) e = cudaMemcpy(device_ptrs[EVG_BIND_TABLES], tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cuda_fail(e, "upload of the loss table");
         sim->tables.loss_tab = (const double*)device_ptrs[EVG_BIND_TABLES];
+        sim->tables.rcp_tab = sim->tables.loss_tab + n_div * evg::kLossD;
+        sim->tables.fast_div = fast && !getenv("EVG_NO_FAST_DIV") ? 1 : 0;
     }
     sim->is_bound = true;
     return EVG_OK;

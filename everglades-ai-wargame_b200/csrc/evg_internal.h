@@ -65,10 +65,14 @@ struct Tables {
     uint8_t edge[kNN][kNN];
     // thread-per-match kernel (evg_step_tpm.cu): per-thread shared-memory row = record + scratch (pitch, in 32-bit
     // words) and a per-warp damage-histogram pool sized for one round of 32 fighting groups
-    int32_t tpm_pitch, tpm_pool_words, tpm_hist16, tpm_pad;
+    int32_t tpm_pitch, tpm_pool_words, tpm_hist16;
+    uint32_t big_mask;  // group lanes (bit L) with more than 8 unit slots
     // lane-pair kernel (evg_step_pair.cu): row pitch and per-side histogram words of its per-match histograms
     int32_t pair_pitch, pair_hwords;
     const double* loss_tab;  // [type][node][bonus][32]: (10.*d)/(armor + bonus*StructureDefense), d < 32
+    const double* rcp_tab;   // [type][node][bonus]: 1 / (armor + bonus*StructureDefense), correctly rounded
+    int32_t fast_div;        // 1: (10.*d)/divisor == the two-FMA correction of (10.*d)*rcp for every reachable d (checked on the host)
+    int32_t max_damage_sum;  // most damage one unit can collect in a turn
 };
 
 constexpr int kLossD = 32;

@@ -40,6 +40,21 @@ __device__ __forceinline__ double np_sum_regs(const double (&hv)[MAXSZ], int siz
     return res;
 }
 
+// (int)(hsum / n) exactly as the reference computes it (int() of the correctly rounded fp64 quotient, server.py:491)
+// for 0 <= hsum <= 100 n, 1 <= n <= 16, without the fp64 division subroutine: q approximates the quotient to 2e-5;
+// if hsum is an exact multiple of n the quotient is that integer; else, unless q is within 1e-3 of an integer, q
+// and the rounded quotient lie strictly between the same two integers.  The division itself remains for the rest.
+__device__ __forceinline__ int int_quotient(double hsum, int n)
+{
+    const double nd = (double)n;
+    const double q = hsum * (double)__frcp_rn((float)n);
+    const int kr = __double2int_rn(q);
+    const double kd = (double)kr;
+    if (__dmul_rn(kd, nd) == hsum) return kr;
+    if (fabs(q - kd) > 1e-3) return (int)q;
+    return (int)__ddiv_rn(hsum, nd);
+}
+
 // 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): a 64-byte health row of 8 units is two requests
 __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d)
 {
@@ -68,7 +83,7 @@ __device__ __forceinline__ void load_group(const double* __restrict__ hp, int si
 template <int MAXSZ, typename HistT>
 __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
                                                 const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
-                                                int* avg_out)
+                                                int* avg_out, double rcp = 0.0)
 {
     // pass 1: damage aimed at every alive unit.  infliction[uid]: uid -> r-th unit alive before combat
     uint32_t dv[MAXSZ];
@@ -81,15 +96,26 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
         rank += on ? 1 : 0;
         dmax = max(dmax, dv[u]);
     }
-    // pass 2: loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601, from the
-    // table of those same fp64 quotients; all lookups are independent and issued together (ltab[0] == 0.0)
+    // pass 2: loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
     double loss[MAXSZ];
+    if (ltab == nullptr) {
+        // without a division or a lookup: a = 10.*dmg exactly (2^52 trick), q0 = a*rcp, then Markstein's correction
+        // fma(fma(-q0, D, a), rcp, q0); the host has checked that this IS a/D for every reachable dmg (Tables::fast_div)
 #pragma unroll
-    for (int u = 0; u < MAXSZ; ++u) loss[u] = dv[u] ? __ldg(ltab + min(dv[u], (uint32_t)(kLossD - 1))) : 0.0;  // no request for unhit units
-    if (dmax >= (uint32_t)kLossD) {  // damage sums beyond the table: the division itself
+        for (int u = 0; u < MAXSZ; ++u) {
+            const double a = __dsub_rn(__hiloint2double(0x43300000, (int)(10u * dv[u])), 4503599627370496.0);
+            const double q0 = __dmul_rn(a, rcp);
+            loss[u] = __fma_rn(__fma_rn(-q0, divisor, a), rcp, q0);
+        }
+    } else {
+        // from the table of those same fp64 quotients; all lookups are independent and issued together (ltab[0] == 0.0)
 #pragma unroll
-        for (int u = 0; u < MAXSZ; ++u)
-            if (dv[u] >= (uint32_t)kLossD) loss[u] = __ddiv_rn(__dmul_rn(10.0, (double)dv[u]), divisor);
+        for (int u = 0; u < MAXSZ; ++u) loss[u] = dv[u] ? __ldg(ltab + min(dv[u], (uint32_t)(kLossD - 1))) : 0.0;  // no request for unhit units
+        if (dmax >= (uint32_t)kLossD) {  // damage sums beyond the table: the division itself
+#pragma unroll
+            for (int u = 0; u < MAXSZ; ++u)
+                if (dv[u] >= (uint32_t)kLossD) loss[u] = __ddiv_rn(__dmul_rn(10.0, (double)dv[u]), divisor);
+        }
     }
     uint32_t alive = alive0;
 #pragma unroll
@@ -107,7 +133,7 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
     for (int u = 0; u < MAXSZ; u += 4)  // one 32-byte store per quad that was hit (padding slots keep what was read)
         if (dv[u] | dv[u + 1] | dv[u + 2] | dv[u + 3]) stg256(hp + u, hv[u], hv[u + 1], hv[u + 2], hv[u + 3]);
     const double hsum = np_sum_regs<MAXSZ>(hv, size);
-    *avg_out = alive ? (int)__ddiv_rn(hsum, (double)__popc(alive)) : 0;  // int((health*1.)/units_alive), :491
+    *avg_out = alive ? int_quotient(hsum, __popc(alive)) : 0;  // int((health*1.)/units_alive), :491
     return alive;
 }
 

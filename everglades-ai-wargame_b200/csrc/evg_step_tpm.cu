@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         // per-thread preparation.  Node words (word-major, X[32 * i]): i = x for player 0 and nn + x for player 1 hold, per node,
         // member mask of the groups present [0:12) | their alive units [16:24) | histogram base of that side [24:32)
         uint32_t fm = 0;          // my match's fighting groups (bit L = side * 12 + gid)
+        uint32_t xm = 0;          // those of them whose second draw block is a work item
         uint32_t b0 = 0, b1 = 0;  // histogram entries per side = alive units of the fighting groups
         if (valid) {
             for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
@@ -260,6 +261,13 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                     b1 += b >> 16;
                 }
             }
+            // a fighting group with more than 8 units alive draws from two Philox blocks: its second block becomes
+            // a work item of its own (a lane running both blocks would hold up its whole round for a second pass)
+            if (S.n_big <= 8)
+                for (uint32_t m = fm & S.big_mask; m; m &= m - 1) {
+                    const int L = __ffs(m) - 1;
+                    if (__popc(R[2 * L + 1] & 0xFFFFu) > 8) xm |= 1u << L;
+                }
             // the health rows of the groups that will fight: start them towards L2 now
             {
                 const char* he = reinterpret_cast<const char*>(A.health + env * S.health_slots);
@@ -273,10 +281,10 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         }
         __syncwarp();  // rows (actions applied, node words) are read by other lanes from here on
         EVG_PHASE_SYNC();
-        // the warp's work list = concatenation of the matches' fighting groups; a round takes whole
-        // matches (a match has <= 24 items), so draws and apply of one match stay in one round and the
+        // the warp's work list = concatenation of the matches' fighting groups (then their second draw blocks); a
+        // round takes whole matches (a match has <= 32 items), so draws and apply of one match stay in one round and the
         // round's histograms fit the warp's pool: match m owns entries [upre[m] - upre[m_begin], +b0+b1)
-        const int nitems = __popc(fm);
+        const int nitems = __popc(fm) + __popc(xm);
         int incl = nitems;
         uint32_t uincl = b0 + b1;
 #pragma unroll
@@ -295,7 +303,12 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             const int nround = __shfl_sync(0xFFFFFFFFu, incl, m_end - 1) - base;
             const uint32_t ubase = __shfl_sync(0xFFFFFFFFu, ub, m_begin) & 0xFFFFu;
             const uint32_t uround = __shfl_sync(0xFFFFFFFFu, uincl, m_end - 1) - ubase;
-            for (uint32_t i = lane; i < (uround * (uint32_t)sizeof(HistT) + 3u) / 4u; i += 32) pool[i] = 0;
+            {
+                const uint32_t zw = (uround * (uint32_t)sizeof(HistT) + 3u) / 4u;
+#pragma unroll
+                for (int j = 0; j < (MAXSZ * (int)sizeof(HistT) * 32 / 4 + 31) / 32; ++j)
+                    if ((uint32_t)(lane + 32 * j) < zw) pool[lane + 32 * j] = 0;
+            }
             const int q = base + lane;
             int m = 0;  // largest m with pre[m] <= q
 #pragma unroll
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 if (cand < 32 && pc <= q) m = cand;
             }
             const int pm = __shfl_sync(0xFFFFFFFFu, pre, m);
-            const uint32_t fmm = __shfl_sync(0xFFFFFFFFu, fm, m);
+            const uint32_t fmm = __shfl_sync(0xFFFFFFFFu, fm, m), xmm = __shfl_sync(0xFFFFFFFFu, xm, m);
             const uint32_t ubm = __shfl_sync(0xFFFFFFFFu, ub, m);
             const bool act = lane < nround;
             // item state kept across the two phases
@@ -315,41 +328,51 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             uint32_t w0 = 0, w1 = 0;
             double hv[MAXSZ];
             double* hp = A.health;
+            const int nf = __popc(fmm);
+            const bool extra = act && q - pm >= nf;  // a second draw block: no health update of its own
+            const bool own_item = act && !extra;
             __syncwarp();  // pool zeroed
             if (act) {
-                L = kth_set_bit(fmm, q - pm);
-                hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
-                load_group<MAXSZ>(hp, S.g_size[L], hv);  // consumed after the draws
+                L = extra ? kth_set_bit(xmm, q - pm - nf) : kth_set_bit(fmm, q - pm);
+                if (!extra) {
+                    hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
+                    load_group<MAXSZ>(hp, S.g_size[L], hv);  // consumed after the draws
+                }
                 side = L >= EVG_NUM_GROUPS ? 1 : 0;
                 const int gg = L - side * EVG_NUM_GROUPS;
                 w0 = Rm[2 * L];
                 w1 = Rm[2 * L + 1];
                 x = (int)(w0 & W0_LOC_MASK);
-                const int cnt = __popc(w1 & 0xFFFFu);
+                const uint32_t cnt = __popc(w1 & 0xFFFFu);
                 const uint32_t own = Xm[32 * (side * nn + x)], opp = Xm[32 * ((1 - side) * nn + x)];
                 const uint32_t n = (opp >> 16) & 0xFFu;                        // opposing units at the node
                 const uint32_t mb = (ubm & 0xFFFFu) - ubase, mb0 = ubm >> 16;  // my match's pool entries; its side-0 count
                 const uint32_t hb = mb + (side ? 0u : mb0) + (opp >> 24);      // opposing histogram base at this node
-                tb = (int)(mb + (side ? mb0 : 0u) + (own >> 24));              // my side's base at this node
-                // my group's range starts after the groups listed before it (arrival order, then gid:
-                // node.groups[pid], :198,690-691); sibling counts are still pre-combat here
-                const uint32_t key = (w1 >> 16) << 4 | (uint32_t)gg;
-                for (uint32_t sm = (own & 0xFFFu) & ~(1u << gg); sm; sm &= sm - 1) {
-                    const int g = __ffs(sm) - 1;
-                    const uint32_t w1g = Rm[2 * (side * EVG_NUM_GROUPS + g) + 1];
-                    if (((w1g >> 16) << 4 | (uint32_t)g) < key) tb += __popc(w1g & 0xFFFFu);
+                if (!extra) {
+                    tb = (int)(mb + (side ? mb0 : 0u) + (own >> 24));          // my side's base at this node
+                    // my group's range starts after the groups listed before it (arrival order, then gid:
+                    // node.groups[pid], :198,690-691); sibling counts are still pre-combat here
+                    const uint32_t key = (w1 >> 16) << 4 | (uint32_t)gg;
+                    for (uint32_t sm = (own & 0xFFFu) & ~(1u << gg); sm; sm &= sm - 1) {
+                        const int g = __ffs(sm) - 1;
+                        const uint32_t w1g = Rm[2 * (side * EVG_NUM_GROUPS + g) + 1];
+                        if (((w1g >> 16) << 4 | (uint32_t)g) < key) tb += __popc(w1g & 0xFFFFu);
+                    }
                 }
                 // draws, :549-566: unit j targets uid = tape(...) among the opposing units at the node and adds
-                // its type's damage to infliction[uid]; 8 draws of 16 bits per Philox block (oracle/tape.py)
+                // its type's damage to infliction[uid]; 8 draws of 16 bits per Philox block (oracle/tape.py).
+                // This item draws for units [8 * jb, 8 * jb + nd)
+                const uint32_t jb = extra ? 1u : 0u;
+                const uint32_t nd = extra ? cnt - 8u : (((xmm >> L) & 1u) ? 8u : cnt);
                 const uint32_t dmg = S.g_damage[L];
                 const uint32_t turn_m = Rm[kRecTurn] + 1u, ep_m = Rm[kRecEpisode];
-                for (int b = 0; 8 * b < cnt; ++b) {
+                for (uint32_t b = jb; 8u * (b - jb) < nd; ++b) {
                     uint32_t r[4];
                     philox4x32_10(S.env_base + (uint32_t)(warp_env0 + m), turn_m,
-                                  (uint32_t)x | (uint32_t)side << 8 | (uint32_t)gg << 16 | (uint32_t)b << 24, ep_m << 8, S.seed_lo, S.seed_hi, r);
+                                  (uint32_t)x | (uint32_t)side << 8 | (uint32_t)gg << 16 | b << 24, ep_m << 8, S.seed_lo, S.seed_hi, r);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (8 * b + k < cnt) {
+                    for (uint32_t k = 0; k < 8; ++k)
+                        if (8u * (b - jb) + k < nd) {
                             const uint32_t half = (k & 1) ? r[k >> 1] >> 16 : r[k >> 1] & 0xFFFFu;
                             const uint32_t idx = hb + ((half * n) >> 16);
                             if (sizeof(HistT) == 1) atomicAdd(&pool[idx >> 2], dmg << ((idx & 3u) * 8));
@@ -359,16 +382,18 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             }
             __syncwarp();
             // apply, :573-643: both sides drew on pre-combat counts (:572); one lane updates one whole group
-            if (act) {
+            if (own_item) {
                 const uint32_t nwd = Rm[kRecNode0 + x - 1];
                 const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
                 const int bonus = (cb == side ? 1 : 0) + ((S.node_flags[x] >> 2) & 1);
                 const int type = S.g_type[L];
                 const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
-                const double* ltab = S.loss_tab + ((size_t)(type * nn + x) * 3 + bonus) * kLossD;
+                const int ti = (type * nn + x) * 3 + bonus;
+                const double* ltab = S.fast_div ? nullptr : S.loss_tab + (size_t)ti * kLossD;
+                const double rcp = S.fast_div ? __ldg(S.rcp_tab + ti) : 0.0;
                 int avg;
                 const uint32_t alive = apply_group<MAXSZ, HistT>(hp, hv, S.g_size[L], w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool), tb,
-                                                                 ltab, divisor, &avg);
+                                                                 ltab, divisor, &avg, rcp);
                 Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
                 Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
             }
