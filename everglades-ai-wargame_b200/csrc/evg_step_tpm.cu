@@ -31,16 +31,19 @@
 
 #include "evg_step_common.cuh"
 
+#ifndef EVG_TPM_SYNC_MASK
+#define EVG_TPM_SYNC_MASK 31
+#endif
 #if EVG_TPM_SYNC == 1
-#define EVG_PHASE_SYNC() __syncthreads()
+#define EVG_PHASE_SYNC(i) do { if ((EVG_TPM_SYNC_MASK >> (i)) & 1) __syncthreads(); } while (0)
 #elif EVG_TPM_SYNC == 2
-#define EVG_PHASE_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kTpmThreads / 4) : "memory")
+#define EVG_PHASE_SYNC(i) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kTpmThreads / 4) : "memory")
 #else
-#define EVG_PHASE_SYNC() ((void)0)
+#define EVG_PHASE_SYNC(i) ((void)0)
 #endif
 
 #ifdef EVG_TPM_SYNC_FINE
-#define EVG_PHASE_SYNC2() EVG_PHASE_SYNC()
+#define EVG_PHASE_SYNC2() EVG_PHASE_SYNC(5)
 #else
 #define EVG_PHASE_SYNC2() ((void)0)
 #endif
@@ -65,30 +68,7 @@ template <int NODES, int MAXSZ, typename HistT, int PITCH>
 __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    // ---- stage the static tables once per CTA
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&T);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    const Tables& S = *reinterpret_cast<const Tables*>(smem);
-    __syncthreads();
-
-    const Geo<NODES> G(S);
-    const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
-    const int P = PITCH ? PITCH : T.tpm_pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
-    // per warp: 32 rows (record + observation staging window), the node words of its 32 matches stored
-    // word-major ([word][lane]: a thread's own accesses always hit bank `lane`, whatever the index), the pool
-    const int WS = 32 * P + 64 * nn + T.tpm_pool_words;
-    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes) + (size_t)warp * WS;  // the warp's 32 rows
-    uint32_t* R = wrow + (size_t)lane * P;  // my record
-    uint32_t* wx = wrow + 32 * P;           // node words of the warp's matches: word i of match m at wx[32 * i + m]
-    uint32_t* X = wx + lane;                // mine: X[32 * i]
-    uint32_t* pool = wx + 64 * nn;          // the warp's histogram pool
-    // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
-    // touches its own 32 rows, so batches need no CTA-wide barrier
     const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
     const bool ext_rows = A.agent[0] == EVG_AGENT_EXTERNAL || A.agent[1] == EVG_AGENT_EXTERNAL;
     // Software pipeline (compile-time map only: 16 chunks of 16 bytes per record): the NEXT batch's records and
@@ -108,7 +88,30 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         for (int k = 0; k < 7; ++k) nxa[k] = ext_rows ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + (e0 + lane) * 7 + k) : 0u;
         return true;
     };
-    if (PIPE) have = request(blockIdx.x);
+    if (PIPE) have = request(blockIdx.x);  // the first batch's records travel while the tables are staged
+    // ---- stage the static tables once per CTA
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&T);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    const Tables& S = *reinterpret_cast<const Tables*>(smem);
+    __syncthreads();
+
+    const Geo<NODES> G(S);
+    const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
+    const int P = PITCH ? PITCH : T.tpm_pitch;
+    const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
+    // per warp: 32 rows (record + observation staging window), the node words of its 32 matches stored
+    // word-major ([word][lane]: a thread's own accesses always hit bank `lane`, whatever the index), the pool
+    const int WS = 32 * P + 64 * nn + T.tpm_pool_words;
+    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes) + (size_t)warp * WS;  // the warp's 32 rows
+    uint32_t* R = wrow + (size_t)lane * P;  // my record
+    uint32_t* wx = wrow + 32 * P;           // node words of the warp's matches: word i of match m at wx[32 * i + m]
+    uint32_t* X = wx + lane;                // mine: X[32 * i]
+    uint32_t* pool = wx + 64 * nn;          // the warp's histogram pool
+    // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
+    // touches its own 32 rows, so batches need no CTA-wide barrier
     for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int64_t warp_env0 = batch * kTpmThreads + warp * 32;
     const int64_t env = warp_env0 + lane;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         }
     }
     __syncwarp();
-    EVG_PHASE_SYNC();
+    EVG_PHASE_SYNC(0);
 
     uint32_t turn = 0, episode = 0;
     int s0 = 0, s1 = 0, status = 0;
@@ -246,9 +249,9 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                     const uint32_t aa = wa.y & 0xFFFFu, ab = wb.y & 0xFFFFu;
                     const bool pa = aa && !(wa.x & W0_MOVING), pb = ab && !(wb.x & W0_MOVING);
                     const uint32_t la = pa ? wa.x & W0_LOC_MASK : 0u, lb = pb ? wb.x & W0_LOC_MASK : 0u;
-                    const uint32_t va = acc0[32 * la], vb = acc1[32 * lb];
-                    acc0[32 * la] = va + (1u << g | (uint32_t)__popc(aa) << 16);
-                    acc1[32 * lb] = vb + (1u << g | (uint32_t)__popc(ab) << 16);
+                    // shared-memory reductions (no value returned): one instruction per update and nothing to wait for
+                    atomicAdd(&acc0[32 * la], 1u << g | (uint32_t)__popc(aa) << 16);
+                    atomicAdd(&acc1[32 * lb], 1u << g | (uint32_t)__popc(ab) << 16);
                 }
             }
             for (int x = 1; x <= n_nodes; ++x) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             }
         }
         __syncwarp();  // rows (actions applied, node words) are read by other lanes from here on
-        EVG_PHASE_SYNC();
+        EVG_PHASE_SYNC(1);
         // the warp's work list = concatenation of the matches' fighting groups (then their second draw blocks); a
         // round takes whole matches (a match has <= 32 items), so draws and apply of one match stay in one round and the
         // round's histograms fit the warp's pool: match m owns entries [upre[m] - upre[m_begin], +b0+b1)
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         }
     }
 
-    EVG_PHASE_SYNC();
+    EVG_PHASE_SYNC(2);
     if (valid) {
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
         //   [0:10) units of all listed groups (:446-449), [10:24) count*control of non-moving groups (:718-724),
@@ -441,9 +444,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 int pa, pb;
                 move(g, va, la, pa);
                 move(EVG_NUM_GROUPS + g, vb, lb, pb);
-                const uint32_t a = acc0[32 * la], b = acc1[32 * lb];  // entry 0 collects the (zero) contributions of dead groups
-                acc0[32 * la] = a + va;
-                acc1[32 * lb] = b + vb;
+                atomicAdd(&acc0[32 * la], va);  // entry 0 collects the (zero) contributions of dead groups
+                atomicAdd(&acc1[32 * lb], vb);
                 s0 += pa;
                 s1 += pb;
             }
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }
 
     if (PIPE) have = request(batch + gridDim.x);
-    EVG_PHASE_SYNC();
+    EVG_PHASE_SYNC(3);
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
     // Each thread packs kTpmStage floats at a time into the staging window of its row; the warp streams the
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }
     __syncwarp();
 
-    EVG_PHASE_SYNC();
+    EVG_PHASE_SYNC(4);
     // ---- cooperative, coalesced store of the records (the padding words are written as zeros)
     {
         const int q4 = RW / 4;
