@@ -31,6 +31,12 @@
 
 #include "evg_step_common.cuh"
 
+#ifndef EVG_TPM_MOVE_UNROLL
+#define EVG_TPM_MOVE_UNROLL 2
+#endif
+#ifndef EVG_TPM_CAPTURE_UNROLL
+#define EVG_TPM_CAPTURE_UNROLL 1
+#endif
 #ifndef EVG_TPM_SYNC_MASK
 #define EVG_TPM_SYNC_MASK 31
 #endif
@@ -52,6 +58,8 @@ namespace evg {
 
 namespace {
 
+constexpr int kMoveUnroll = EVG_TPM_MOVE_UNROLL, kCaptureUnroll = EVG_TPM_CAPTURE_UNROLL;
+
 // game_init state (server.py:133-209) for one match: record row in shared memory + health refill
 __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* health, int n_nodes)
 {
@@ -69,6 +77,9 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // chunk of a 512-byte pair of records a lane moves in the whole-warp copies: lane bits 3 and 4 swapped, so that a
+    // half-warp covers chunks 0..7 (or 8..15) of BOTH records and its 8-byte row accesses fall into 16 different bank pairs
+    const int pl = (lane & 7) | ((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 4;
     const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
     const bool ext_rows = A.agent[0] == EVG_AGENT_EXTERNAL || A.agent[1] == EVG_AGENT_EXTERNAL;
     // Software pipeline (compile-time map only: 16 chunks of 16 bytes per record): the NEXT batch's records and
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         if (b >= nbatches || e0 + 32 > A.n_envs) return false;  // partial warps take the direct path
         const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + e0 * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) nxt[i] = __ldcs(g4 + lane + 32 * i);
+        for (int i = 0; i < 16; ++i) nxt[i] = __ldcs(g4 + pl + 32 * i);
 #pragma unroll
         for (int k = 0; k < 7; ++k) nxa[k] = ext_rows ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + (e0 + lane) * 7 + k) : 0u;
         return true;
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         for (int k = 0; k < 7; ++k) aw[k] = nxa[k];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int f = lane + 32 * i, m = f >> 4, q = f & 15;
+            const int f = pl + 32 * i, m = f >> 4, q = f & 15;
             uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
             d[0] = make_uint2(nxt[i].x, nxt[i].y);
             if (4 * q + 2 < RWU) d[1] = make_uint2(nxt[i].z, nxt[i].w);  // the record's padding words are not kept
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 pts = (int)cnt * (int)S.g_cost[L];
                 any_alive |= live;
             };
-#pragma unroll 2
+#pragma unroll kMoveUnroll
             for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
                 uint32_t va, la, vb, lb;
                 int pa, pb;
@@ -453,6 +464,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
 
         // ---- capture (server.py:708-767; current_turn > 0 here) and node scoring (server.py:298-310)
         bool basecap = false;
+#pragma unroll kCaptureUnroll
         for (int n = 1; n <= n_nodes; ++n) {
             const uint32_t nw = R[kRecNode0 + n - 1];
             int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
@@ -623,7 +635,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         };
         if (NODES && nvalid == 32) {
 #pragma unroll
-            for (int i = 0; i < (NODES ? 16 : 1); ++i) put(lane + 32 * i);
+            for (int i = 0; i < (NODES ? 16 : 1); ++i) put(pl + 32 * i);
         } else {
 #pragma unroll 1
             for (int f = lane; f < total; f += 32) put(f);
