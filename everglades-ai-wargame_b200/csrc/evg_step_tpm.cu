@@ -72,7 +72,9 @@ __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* hea
     for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
 }
 
-template <int NODES, int MAXSZ, typename HistT, int PITCH>
+// AGENTS: the instantiation that can generate scripted players' rows itself (evg_step_agents); the plain step
+// leaves that code out, the kernel's instruction footprint being what its instruction cache misses are made of
+template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS>
 __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -111,12 +113,30 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
 
     const Geo<NODES> G(S);
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
+    // the observation entries that never change (a third of them: the nodes' DEFENSE/OBSERVE flags in each viewer's
+    // numbering and the groups' unit types) are converted once per CTA; packing copies them from here
+    float* oconst = reinterpret_cast<float*>(smem + T.sm_tables_bytes);
+    const int oc_bytes = (2 * OL * 4 + 15) & ~15;
+    for (int f = threadIdx.x; f < 2 * OL; f += blockDim.x) {
+        const int p = f >= OL ? 1 : 0, i = f - p * OL;
+        float v = 0.f;
+        if (i >= 1 && i < 1 + 4 * n_nodes) {
+            const int k = (i - 1) >> 2, j = (i - 1) & 3;
+            const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
+            if (j < 2) v = (float)((S.node_flags[x] >> j) & 1u);
+        } else if (i >= 1 + 4 * n_nodes) {
+            const int q = i - 1 - 4 * n_nodes, g = q / 5;
+            if (q - 5 * g == 1) v = (float)S.g_type[p * EVG_NUM_GROUPS + g];
+        }
+        oconst[f] = v;
+    }
+    __syncthreads();
     const int P = PITCH ? PITCH : T.tpm_pitch;
     const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
     // per warp: 32 rows (record + observation staging window), the node words of its 32 matches stored
     // word-major ([word][lane]: a thread's own accesses always hit bank `lane`, whatever the index), the pool
     const int WS = 32 * P + 64 * nn + T.tpm_pool_words;
-    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes) + (size_t)warp * WS;  // the warp's 32 rows
+    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes + oc_bytes) + (size_t)warp * WS;  // the warp's 32 rows
     uint32_t* R = wrow + (size_t)lane * P;  // my record
     uint32_t* wx = wrow + 32 * P;           // node words of the warp's matches: word i of match m at wx[32 * i + m]
     uint32_t* X = wx + lane;                // mine: X[32 * i]
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             uint32_t rows[2 * EVG_MAX_ACTIONS];
 #pragma unroll
             for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) rows[r] = (aw[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
-            if (A.agent[0] != EVG_AGENT_EXTERNAL || A.agent[1] != EVG_AGENT_EXTERNAL) {
+            if (AGENTS && (A.agent[0] != EVG_AGENT_EXTERNAL || A.agent[1] != EVG_AGENT_EXTERNAL)) {
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl)
                     if (A.agent[pl] == EVG_AGENT_RANDOM)
@@ -555,8 +575,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             if (i < 1 + 4 * n_nodes) {
                 const int k = (i - 1) >> 2, j = (i - 1) & 3;
                 const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
-                if (j == 0) return (float)(S.node_flags[x] & 1u);
-                if (j == 1) return (float)((S.node_flags[x] >> 1) & 1u);
+                if (j < 2) return oconst[f];  // 'DEFENSE' / 'OBSERVE' in resource, :442-443
                 if (j == 2) return (float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu);  // raw sign for both viewers
                 return (float)(X[32 * ((p ? 0 : nn) + x)] & 1023u);                                  // opposing listed units
             }
@@ -564,7 +583,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             const int L = p * EVG_NUM_GROUPS + g;
             const uint32_t w0 = R[2 * L];
             if (j == 0) return (float)(p ? (uint32_t)S.p1_map[w0 & W0_LOC_MASK] : (w0 & W0_LOC_MASK));
-            if (j == 1) return (float)S.g_type[L];
+            if (j == 1) return oconst[f];  // unit type id
             if (j == 2) return (float)((w0 >> W0_AVG_SHIFT) & 127u);
             if (j == 3) return (float)((w0 >> 21) & 1u);
             return (float)__popc(R[2 * L + 1] & 0xFFFFu);
@@ -661,31 +680,40 @@ Variant pick(const Tables& t)
 
 cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
 {
-    size_t smem = (size_t)t.sm_tables_bytes + (size_t)(kTpmThreads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
+    size_t smem = (size_t)t.sm_tables_bytes + (size_t)((2 * t.obs_len * 4 + 15) & ~15) +
+                  (size_t)(kTpmThreads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
     cudaError_t e;
-
-    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+#define EVG_TPM_EACH(F)                                         \
+    F((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false>)) \
+    F((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true>))  \
+    F((evg_step_tpm_kernel<0, 16, uint8_t, 0, true>))            \
+    F((evg_step_tpm_kernel<0, 16, uint16_t, 0, true>))
+#define EVG_TPM_ATTR(K) \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    EVG_TPM_EACH(EVG_TPM_ATTR)
+#undef EVG_TPM_ATTR
     switch (pick(t)) {
-        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch>, kTpmThreads, smem); break;
-        case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint8_t, 0>, kTpmThreads, smem); break;
-        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint16_t, 0>, kTpmThreads, smem); break;
+        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false>, kTpmThreads, smem); break;
+        case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint8_t, 0, true>, kTpmThreads, smem); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint16_t, 0, true>, kTpmThreads, smem); break;
     }
-    if (e != cudaSuccess) return e;
-    return cudaSuccess;
+    return e;
 }
 
 cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream)
 {
     const int64_t nb = (a.n_envs + kTpmThreads - 1) / kTpmThreads;
     const unsigned grid = (unsigned)(nb < max_grid ? nb : max_grid);
+    const bool agents = a.agent[0] != EVG_AGENT_EXTERNAL || a.agent[1] != EVG_AGENT_EXTERNAL;
     switch (pick(t)) {
-        case V_FAST: evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
-        case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
-        default: evg_step_tpm_kernel<0, 16, uint16_t, 0><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        case V_FAST:
+            if (agents) evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true><<<grid, kTpmThreads, smem, stream>>>(t, a);
+            else evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false><<<grid, kTpmThreads, smem, stream>>>(t, a);
+            break;
+        case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0, true><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        default: evg_step_tpm_kernel<0, 16, uint16_t, 0, true><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
     }
     return cudaGetLastError();
 }
