@@ -203,6 +203,28 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
         t.tpm_pitch = pitch;
         t.tpm_pool_words = (32 * round_up(max_size, 4) * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
     }
+    // The step kernel forms (10.*d)/D without a division: q0 = a*r with r = 1/D, then q = fma(fma(-q0, D, a), r, q0)
+    // (Markstein's correction).  It is used only if it reproduces a/D for EVERY reachable numerator a = 10*d of
+    // every divisor D = armor + bonus*StructureDefense, which is checked here exhaustively.
+    {
+        bool fast = !getenv("EVG_NO_FAST_DIV");
+        for (int k = 0; k < c.n_unit_types && fast; ++k)
+            for (int x = 1; x <= c.n_nodes && fast; ++x)
+                for (int b = 0; b < 3 && fast; ++b) {
+                    volatile double node_def = (double)b * c.node_defense[x];
+                    volatile double divisor = c.unit_armor[k] + node_def;
+                    volatile double r = 1.0 / divisor;
+                    for (int d = 1; d <= t.max_damage_sum && fast; ++d) {
+                        volatile double a = 10.0 * (double)d;
+                        volatile double q0 = a * r;
+                        volatile double rem = fma(-q0, divisor, a);
+                        volatile double q = fma(rem, r, q0);
+                        volatile double ref = a / divisor;
+                        if (!(q == ref)) fast = false;
+                    }
+                }
+        t.fast_div = fast ? 1 : 0;
+    }
     *out = t;
     return EVG_OK;
 }
@@ -363,10 +385,7 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
         const int nn = c.n_nodes + 1;
         const size_t n_div = (size_t)c.n_unit_types * nn * 3;
         std::vector<double> tab(n_div * (evg::kLossD + 1), 0.0);
-        // ... followed by the reciprocal of every divisor.  The kernel then forms the quotient without a division:
-        // q0 = a*r, q = fma(fma(-q0, D, a), r, q0) (Markstein's correction), used only if it reproduces a/D for
-        // EVERY reachable numerator a = 10*d of every divisor D, which is checked here exhaustively
-        bool fast = true;
+        // ... followed by the reciprocal of every divisor (Tables::fast_div, build_tables)
         for (int t = 0; t < c.n_unit_types; ++t)
             for (int x = 1; x <= c.n_nodes; ++x)
                 for (int b = 0; b < 3; ++b) {
@@ -379,21 +398,12 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
                     }
                     volatile double r = 1.0 / divisor;
                     tab[n_div * evg::kLossD + ti] = r;
-                    for (int d = 1; d <= sim->tables.max_damage_sum && fast; ++d) {
-                        volatile double a = 10.0 * (double)d;
-                        volatile double q0 = a * r;
-                        volatile double rem = fma(-q0, divisor, a);
-                        volatile double q = fma(rem, r, q0);
-                        volatile double ref = a / divisor;
-                        if (!(q == ref)) fast = false;
-                    }
                 }
         cudaError_t e = cudaSetDevice(sim->device);
         if (e == cudaSuccess) e = cudaMemcpy(device_ptrs[EVG_BIND_TABLES], tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cuda_fail(e, "upload of the loss table");
         sim->tables.loss_tab = (const double*)device_ptrs[EVG_BIND_TABLES];
         sim->tables.rcp_tab = sim->tables.loss_tab + n_div * evg::kLossD;
-        sim->tables.fast_div = fast && !getenv("EVG_NO_FAST_DIV") ? 1 : 0;
     }
     sim->is_bound = true;
     return EVG_OK;

@@ -80,7 +80,7 @@ __device__ __forceinline__ void load_group(const double* __restrict__ hp, int si
 
 // One target group: apply the damage histogram to its units, write the touched quads back.  Returns the new
 // alive mask and the observation's avg health (server.py:573-643, :480-491).
-template <int MAXSZ, typename HistT>
+template <int MAXSZ, typename HistT, bool FMA_ONLY = false>
 __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
                                                 const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
                                                 int* avg_out, double rcp = 0.0)
@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
     }
     // pass 2: loss = (10.*dmg)/(armor + (tgt_cntrl + fort_bns)*StructureDefense), server.py:592-601
     double loss[MAXSZ];
-    if (ltab == nullptr) {
+    if (FMA_ONLY || ltab == nullptr) {
         // without a division or a lookup: a = 10.*dmg exactly (2^52 trick), q0 = a*rcp, then Markstein's correction
         // fma(fma(-q0, D, a), rcp, q0); the host has checked that this IS a/D for every reachable dmg (Tables::fast_div)
 #pragma unroll

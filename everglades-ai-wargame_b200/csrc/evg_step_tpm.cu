@@ -72,6 +72,52 @@ __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* hea
     for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
 }
 
+// finished matches of a warp -> the global counters (rare: kept out of the kernel's hot instruction stream)
+__device__ __noinline__ void episode_stats(unsigned long long* stats, bool reset_now, int s0, int s1, uint32_t turn, int status, int lane)
+{
+    const unsigned e = reset_now ? 1u : 0u;
+    const unsigned v[ST_COUNT] = {e, e && s0 > s1, e && s1 > s0, e && s0 == s1, e ? turn : 0u, e ? (unsigned)s0 : 0u,
+                                  e ? (unsigned)s1 : 0u, e && status == 0, e && status == 1, e && status == 2, e && status == 3};
+#pragma unroll
+    for (int k = 0; k < ST_COUNT; ++k) {
+        const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+        if (lane == 0 && sum) atomicAdd(&stats[k], (unsigned long long)sum);
+    }
+}
+
+// records and action rows of a warp's matches straight from global memory into its rows: the path of partial warps
+// and of the run-time-sized maps (the compile-time map takes them from the registers of its software pipeline)
+template <int NODES>
+__device__ __noinline__ void load_rows_direct(const StepArgs& A, uint32_t* wrow, int P, int RW, int RWU, int64_t warp_env0, int nvalid,
+                                              int lane, bool prefetch_next, int64_t next_env0)
+{
+    if (prefetch_next && next_env0 + 32 <= A.n_envs) {  // pull the NEXT batch's records and action rows towards L2
+        const char* nr = reinterpret_cast<const char*>(A.records) + next_env0 * RW * 4;
+        for (int b = lane * 128; b < 32 * RW * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + b));
+        const char* na = reinterpret_cast<const char*>(A.actions) + next_env0 * 28;
+        if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(na + lane * 128));
+    }
+    const int q4 = RW / 4;  // 16-byte chunks per record
+    const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + warp_env0 * q4;
+    const int total = nvalid * q4;
+#pragma unroll 1
+    for (int f0 = 0; f0 < total; f0 += 32 * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = f0 + 32 * i + lane < total ? __ldcs(g4 + f0 + 32 * i + lane) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = f0 + 32 * i + lane;
+            if (f < total) {
+                const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
+                uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
+                if (NODES || 4 * q < RWU) d[0] = make_uint2(v[i].x, v[i].y);
+                if (4 * q + 2 < RWU) d[1] = make_uint2(v[i].z, v[i].w);  // the record's padding words are not kept
+            }
+        }
+    }
+}
+
 // AGENTS: the instantiation that can generate scripted players' rows itself (evg_step_agents); the plain step
 // leaves that code out, the kernel's instruction footprint being what its instruction cache misses are made of
 template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS>
@@ -162,39 +208,11 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             if (4 * q + 2 < RWU) d[1] = make_uint2(nxt[i].z, nxt[i].w);  // the record's padding words are not kept
         }
     } else {
-        if (!PIPE) {  // pull the NEXT batch's records and action rows towards L2 while this one is processed
-            const int64_t nenv0 = warp_env0 + (int64_t)gridDim.x * kTpmThreads;
-            if (nenv0 + 32 <= A.n_envs) {
-                const char* nr = reinterpret_cast<const char*>(A.records) + nenv0 * RW * 4;
-                for (int b = lane * 128; b < 32 * RW * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + b));
-                const char* na = reinterpret_cast<const char*>(A.actions) + nenv0 * 28;
-                if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(na + lane * 128));
-            }
-        }
-        // action rows requested before the records so the latencies overlap
+        // ---- cooperative, coalesced load of the warp's records into the per-thread rows
+        // (action rows requested before the records so the latencies overlap)
 #pragma unroll
         for (int k = 0; k < 7; ++k) aw[k] = (valid && ext_rows) ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
-
-        // ---- cooperative, coalesced load of the warp's records into the per-thread rows
-        const int q4 = RW / 4;  // 16-byte chunks per record
-        const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + warp_env0 * q4;
-        const int total = nvalid * q4;
-#pragma unroll 1
-        for (int f0 = 0; f0 < total; f0 += 32 * 4) {
-            uint4 v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = f0 + 32 * i + lane < total ? __ldcs(g4 + f0 + 32 * i + lane) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int f = f0 + 32 * i + lane;
-                if (f < total) {
-                    const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
-                    uint2* d = reinterpret_cast<uint2*>(wrow + (size_t)m * P + 4 * q);
-                    if (NODES || 4 * q < RWU) d[0] = make_uint2(v[i].x, v[i].y);
-                    if (4 * q + 2 < RWU) d[1] = make_uint2(v[i].z, v[i].w);
-                }
-            }
-        }
+        load_rows_direct<NODES>(A, wrow, P, RW, RWU, warp_env0, nvalid, lane, !PIPE, warp_env0 + (int64_t)gridDim.x * kTpmThreads);
     }
     __syncwarp();
     EVG_PHASE_SYNC(0);
@@ -423,11 +441,12 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 const int type = S.g_type[L];
                 const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const int ti = (type * nn + x) * 3 + bonus;
-                const double* ltab = S.fast_div ? nullptr : S.loss_tab + (size_t)ti * kLossD;
-                const double rcp = S.fast_div ? __ldg(S.rcp_tab + ti) : 0.0;
+                constexpr bool FMA_ONLY = NODES != 0;  // the compile-time map's kernel is only picked when Tables::fast_div holds
+                const double* ltab = FMA_ONLY || S.fast_div ? nullptr : S.loss_tab + (size_t)ti * kLossD;
+                const double rcp = FMA_ONLY || S.fast_div ? __ldg(S.rcp_tab + ti) : 0.0;
                 int avg;
-                const uint32_t alive = apply_group<MAXSZ, HistT>(hp, hv, S.g_size[L], w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool), tb,
-                                                                 ltab, divisor, &avg, rcp);
+                const uint32_t alive = apply_group<MAXSZ, HistT, FMA_ONLY>(hp, hv, S.g_size[L], w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
+                                                                           tb, ltab, divisor, &avg, rcp);
                 Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
                 Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
             }
@@ -535,16 +554,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }
     const bool reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
     // ---- episode end: statistics, aggregated over the warp before touching the global counters
-    if (__any_sync(0xFFFFFFFFu, reset_now)) {
-        const unsigned e = reset_now ? 1u : 0u;
-        const unsigned v[ST_COUNT] = {e, e && s0 > s1, e && s1 > s0, e && s0 == s1, e ? turn : 0u, e ? (unsigned)s0 : 0u,
-                                      e ? (unsigned)s1 : 0u, e && status == 0, e && status == 1, e && status == 2, e && status == 3};
-#pragma unroll
-        for (int k = 0; k < ST_COUNT; ++k) {
-            const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, v[k]);
-            if (lane == 0 && sum) atomicAdd(&A.stats[k], (unsigned long long)sum);
-        }
-    }
+    if (__any_sync(0xFFFFFFFFu, reset_now)) episode_stats(A.stats, reset_now, s0, s1, turn, status, lane);
     if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
         reset_row(S, R, A.health + env * S.health_slots, n_nodes);
         turn = 0;
@@ -672,7 +682,7 @@ enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
 
 Variant pick(const Tables& t)
 {
-    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == kFastPitch) return V_FAST;
+    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == kFastPitch && t.fast_div) return V_FAST;
     return t.tpm_hist16 ? V_GENERIC16 : V_GENERIC8;
 }
 
