@@ -38,7 +38,7 @@
 #define EVG_TPM_CAPTURE_UNROLL 1
 #endif
 #ifndef EVG_TPM_SYNC_MASK
-#define EVG_TPM_SYNC_MASK 31
+#define EVG_TPM_SYNC_MASK 8  // which of the phase boundaries carry a CTA barrier: bit 3 = before the observation phase (measured best, profiles/README.md)
 #endif
 #if EVG_TPM_SYNC == 1
 #define EVG_PHASE_SYNC(i) do { if ((EVG_TPM_SYNC_MASK >> (i)) & 1) __syncthreads(); } while (0)
@@ -48,10 +48,11 @@
 #define EVG_PHASE_SYNC(i) ((void)0)
 #endif
 
-#ifdef EVG_TPM_SYNC_FINE
-#define EVG_PHASE_SYNC2() EVG_PHASE_SYNC(5)
-#else
-#define EVG_PHASE_SYNC2() ((void)0)
+#ifndef EVG_TPM_REQUEST_AT
+#define EVG_TPM_REQUEST_AT 1  // where the next batch's records are requested: 0 before the observation phase, 1 before movement
+#endif
+#ifndef EVG_TPM_SYNC_OBS_CHUNK
+#define EVG_TPM_SYNC_OBS_CHUNK 3
 #endif
 
 namespace evg {
@@ -61,7 +62,7 @@ namespace {
 constexpr int kMoveUnroll = EVG_TPM_MOVE_UNROLL, kCaptureUnroll = EVG_TPM_CAPTURE_UNROLL;
 
 // game_init state (server.py:133-209) for one match: record row in shared memory + health refill
-__device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* health, int n_nodes)
+__device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* health, int n_nodes, uint32_t* X = nullptr)
 {
     for (int L = 0; L < kGroupLanes; ++L) {
         R[2 * L] = S.init_w0[L];
@@ -70,6 +71,14 @@ __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* hea
     for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
     double2* hp = reinterpret_cast<double2*>(health);
     for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
+    if (X) {  // EVG_AUTORESET_NEXT: the observation shows the new match, so its node sums are needed too
+        const int nn = n_nodes + 1;
+        for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
+        for (int L = 0; L < kGroupLanes; ++L) {
+            const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
+            X[32 * ((L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK))] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;
+        }
+    }
 }
 
 // finished matches of a warp -> the global counters (rare: kept out of the kernel's hot instruction stream)
@@ -456,6 +465,9 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     }
 
     EVG_PHASE_SYNC(2);
+#if EVG_TPM_REQUEST_AT == 1
+    if (PIPE) have = request(batch + gridDim.x);
+#endif
     if (valid) {
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
         //   [0:10) units of all listed groups (:446-449), [10:24) count*control of non-moving groups (:718-724),
@@ -556,17 +568,14 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     // ---- episode end: statistics, aggregated over the warp before touching the global counters
     if (__any_sync(0xFFFFFFFFu, reset_now)) episode_stats(A.stats, reset_now, s0, s1, turn, status, lane);
     if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
-        reset_row(S, R, A.health + env * S.health_slots, n_nodes);
+        reset_row(S, R, A.health + env * S.health_slots, n_nodes, X);
         turn = 0;
         episode += 1;
-        for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
-        for (int L = 0; L < kGroupLanes; ++L) {
-            const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
-            X[32 * ((L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK))] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;
-        }
     }
 
-    if (PIPE) have = request(batch + gridDim.x);
+#if EVG_TPM_REQUEST_AT == 0
+    if (PIPE) have = request(batch + gridDim.x);  // in flight across the barrier
+#endif
     EVG_PHASE_SYNC(3);
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
@@ -611,7 +620,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                     if (SP * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
             }
             __syncwarp();
-            EVG_PHASE_SYNC2();
+            if (c == EVG_TPM_SYNC_OBS_CHUNK) EVG_PHASE_SYNC(5);
             const int pr = SP * c + cp;
             if (pr < npairs) {
                 const uint32_t* srow = wrow + stage_off + 2 * cp;
