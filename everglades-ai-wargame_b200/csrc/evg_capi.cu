@@ -54,6 +54,7 @@ struct EvgSim {
     EvgLayout layout;
     bool use_tpm;     // a row-based step kernel (tpm / pair) or the warp-per-match one (EVG_STEP_KERNEL=warp)
     bool use_pair;    // two lanes per match (EVG_STEP_KERNEL=pair) instead of one thread per match (=tpm)
+    const uint4* tables_dev;  // Tables in device memory (inside bind slot EVG_BIND_TABLES)
     size_t tpm_smem;
     int tpm_grid;  // persistent CTAs: SMs x resident CTAs
     size_t pair_smem;
@@ -350,7 +351,8 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
     L.stats_bytes = evg::ST_COUNT * 8;
     L.agents_bytes = n_envs * 16;
-    L.tables_bytes = (int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8;  // loss table, then reciprocals
+    // loss table, then reciprocals, then the Tables struct itself (the step kernel stages it from here)
+    L.tables_bytes = round_up((int)((int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8), 16) + round_up((int)sizeof(evg::Tables), 16);
     *out = s;
     return EVG_OK;
 }
@@ -404,6 +406,10 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
         if (e != cudaSuccess) return cuda_fail(e, "upload of the loss table");
         sim->tables.loss_tab = (const double*)device_ptrs[EVG_BIND_TABLES];
         sim->tables.rcp_tab = sim->tables.loss_tab + n_div * evg::kLossD;
+        char* tdev = (char*)device_ptrs[EVG_BIND_TABLES] + round_up((int)(tab.size() * sizeof(double)), 16);
+        e = cudaMemcpy(tdev, &sim->tables, sizeof(evg::Tables), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "upload of the static tables");
+        sim->tables_dev = (const uint4*)tdev;
     }
     sim->is_bound = true;
     return EVG_OK;
@@ -444,6 +450,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.status = d_status;
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
+    a.tables_dev = sim->tables_dev;
     cudaError_t e = !sim->use_tpm  ? evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream)
                     : sim->use_pair ? evg::launch_step_pair(sim->tables, a, sim->pair_smem, sim->pair_grid, (cudaStream_t)stream)
                                     : evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);

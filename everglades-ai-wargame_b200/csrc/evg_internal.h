@@ -36,7 +36,7 @@ constexpr uint32_t W0_MOVING = 1u << 21;
 constexpr int W0_AVG_SHIFT = 24;
 
 // Static tables, passed to every kernel by value (__grid_constant__) and staged in shared memory.
-struct Tables {
+struct alignas(16) Tables {
     int32_t n_nodes, obs_len, rec_words8, health_slots;
     int32_t turn_limit, capture_bonus, auto_reset, max_group_size;
     int32_t has_small_groups, hist_words, n_big, pad1;  // hist_words: u32 words per side of the damage histogram
@@ -111,6 +111,7 @@ struct StepArgs {
     int64_t n_envs;
     int32_t agent[2];      // EVG_AGENT_*: where each player's action rows come from
     int8_t* actions_out;   // optional: rows generated by scripted agents are also written here
+    const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
 };
 
 // launchers (evg_kernels.cu); all asynchronous on `stream`, return the launch error

@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     };
     if (PIPE) have = request(blockIdx.x);  // the first batch's records travel while the tables are staged
     // ---- stage the static tables once per CTA
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&T);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    {   // from device memory with coalesced 16-byte loads (per-lane addresses into the parameter bank would be serialised)
+        static_assert(sizeof(Tables) % 16 == 0, "Tables is copied in 16-byte pieces");
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 16); i += blockDim.x) dst[i] = __ldg(A.tables_dev + i);
     }
     const Tables& S = *reinterpret_cast<const Tables*>(smem);
     __syncthreads();
