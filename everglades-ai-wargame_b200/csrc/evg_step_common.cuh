@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
     uint32_t alive = alive0;
 #pragma unroll
     for (int u = 0; u < MAXSZ; ++u) {
-        if (dv[u]) {
+        if (FMA_ONLY || dv[u]) {  // (an unhit unit loses 0.0; dead and padding slots hold 0.0 or stay positive: both no-ops)
             double h = __dsub_rn(hv[u], loss[u]);  // server.py:609
             if (h <= 0.0) {                        // server.py:615-618
                 h = 0.0;
