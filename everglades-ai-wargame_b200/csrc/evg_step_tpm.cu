@@ -665,7 +665,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             const int m = NODES ? f >> 4 : f / q4, q = NODES ? f & 15 : f % q4;
             const uint32_t* sw = wrow + (size_t)m * P + 4 * q;
             uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
-            if (NODES || 4 * q < RWU) a = *reinterpret_cast<const uint2*>(sw);
+            if (NODES || 4 * q < RWU)  // (asm: one 8-byte load; the compiler would split it around the zeroing of a.y below)
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"((uint32_t)__cvta_generic_to_shared(sw)));
             if (4 * q + 2 < RWU) b = *reinterpret_cast<const uint2*>(sw + 2);
             if (4 * q + 1 >= used) a.y = 0u;
             if (4 * q + 3 >= used) b.y = 0u;
