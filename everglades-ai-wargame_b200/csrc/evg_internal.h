@@ -88,7 +88,7 @@ constexpr int kTpmThreads = EVG_TPM_THREADS;
 #define EVG_TPM_MIN_CTAS 3
 #endif
 #ifndef EVG_TPM_SYNC
-#define EVG_TPM_SYNC 1  // the warps of a CTA pass the phases together (0: free-running, 1: all warps, 2: the warps of one scheduler)
+#define EVG_TPM_SYNC 1  // CTA barriers at the phase boundaries named by EVG_TPM_SYNC_MASK (0: free-running warps)
 #endif
 #ifndef EVG_TPM_PIPE
 #define EVG_TPM_PIPE 1

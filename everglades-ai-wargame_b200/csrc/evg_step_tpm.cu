@@ -13,17 +13,25 @@
 // Memory behaviour stays that of the warp kernel — HBM sees the same bytes:
 //   * the 256-byte records of a warp's 32 matches are loaded/stored COOPERATIVELY (coalesced 16-byte
 //     accesses) into per-thread rows of shared memory; row pitch P has P/2 odd, so "every thread reads
-//     word w of its own row" is bank-conflict free for 4- and 8-byte accesses;
+//     word w of its own row" is bank-conflict free for 4- and 8-byte accesses.  The loads are a SOFTWARE
+//     PIPELINE: the next batch's records are requested into registers while this batch is still being
+//     processed, so no batch starts with an exposed DRAM round trip;
 //   * observations are packed by each thread into a 128-byte staging window of its row and streamed
 //     out by the warp as contiguous float2 runs (two matches per store instruction);
 //   * unit health is read as whole 64/96-byte group rows (full 32-byte sectors), only for groups that
 //     fight, and only hit units are written back.
-// Scratch per thread (dynamic indexing needs addressable storage): two words per node (member masks and unit
-// totals in combat, capture accumulators afterwards) and the observation staging window.  The damage
-// histograms of a combat round live in a per-WARP pool (a round is <= 32 fighting groups, so <= 32 x 12
-// entries), which keeps the row at 102 words and lets 4 CTAs (16 warps) share an SM.  IEEE fp64 health
-// arithmetic as in the reference; the per-hit division is a lookup in a host-built table of the SAME fp64
-// quotients for damage sums < 32.
+// Per warp besides the rows: two words per node and match, stored word-major (bank = lane for any dynamic
+// index: member masks and unit totals in combat, capture accumulators afterwards), and a pool for the damage
+// histograms of one combat round (a round is <= 32 work items, so <= 32 x 12 entries).  IEEE fp64 health
+// arithmetic as in the reference; the per-hit quotient is a reciprocal and two FMAs where the host has proved
+// that exact (Tables::fast_div), else a table of the same fp64 quotients / the division itself.
+//
+// Instruction fetch matters as much as data here (profiles/README.md): three CTAs per SM walk a ~90 KB kernel
+// independently, so (1) ONE CTA barrier per batch, before the observation phase, keeps a CTA's four warps on the
+// same instructions through the longest straight-line code, (2) code that a launch never executes lives in
+// another instantiation (AGENTS) or out of line (statistics, partial warps, resets), (3) loops stay rolled where
+// unrolling buys little.  The knobs below exist for A/B builds (tools/build_variant.sh); defaults are the
+// measured best.
 //
 // Reference semantics are cited per phase (server.py / env.py as in evg_kernels.cu); the checker is
 // oracle/evg_oracle.c.
@@ -40,19 +48,14 @@
 #ifndef EVG_TPM_SYNC_MASK
 #define EVG_TPM_SYNC_MASK 8  // which of the phase boundaries carry a CTA barrier: bit 3 = before the observation phase (measured best, profiles/README.md)
 #endif
-#if EVG_TPM_SYNC == 1
+#if EVG_TPM_SYNC
 #define EVG_PHASE_SYNC(i) do { if ((EVG_TPM_SYNC_MASK >> (i)) & 1) __syncthreads(); } while (0)
-#elif EVG_TPM_SYNC == 2
-#define EVG_PHASE_SYNC(i) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kTpmThreads / 4) : "memory")
 #else
 #define EVG_PHASE_SYNC(i) ((void)0)
 #endif
 
 #ifndef EVG_TPM_REQUEST_AT
 #define EVG_TPM_REQUEST_AT 1  // where the next batch's records are requested: 0 before the observation phase, 1 before movement
-#endif
-#ifndef EVG_TPM_SYNC_OBS_CHUNK
-#define EVG_TPM_SYNC_OBS_CHUNK 3
 #endif
 
 namespace evg {
@@ -620,7 +623,6 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                     if (SP * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
             }
             __syncwarp();
-            if (c == EVG_TPM_SYNC_OBS_CHUNK) EVG_PHASE_SYNC(5);
             const int pr = SP * c + cp;
             if (pr < npairs) {
                 const uint32_t* srow = wrow + stage_off + 2 * cp;

@@ -86,6 +86,7 @@ def test_null_handle_calls_fail(lib):
     assert lib.evg_reset(None, None, None, None) == -1
     assert lib.evg_destroy(None) == -1
     assert lib.evg_launch_count(None) == -1
+    assert lib.evg_step_kernel_kind(None) == -1
 
 
 def test_json_loader_semantics(tmp_path):

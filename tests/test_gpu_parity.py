@@ -344,3 +344,31 @@ def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg):
         assert_states_equal(env.get_state(), ora.states, "end")
     finally:
         cfg.auto_reset = 0
+
+
+def test_loss_quotient_paths_agree(evg, eo, cfg, monkeypatch):
+    """The thread-per-match kernel forms (10.*dmg)/divisor as reciprocal + two FMAs when evg_create has proved that
+    equal to the IEEE quotient for every reachable dmg (Tables::fast_div); EVG_NO_FAST_DIV forces the generic
+    instantiation with the loss table / division.  Both must reproduce the oracle's fp64 health bit for bit."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
+    rng = np.random.default_rng(77)
+    for no_fast in ("", "1"):
+        if no_fast:
+            monkeypatch.setenv("EVG_NO_FAST_DIV", no_fast)
+        run_against_oracle(evg, eo, cfg, 700, 110, seed=23, first=3, make_actions=lambda s: adjacent_actions(rng, s, cfg))
+
+
+def test_step_kernel_kind_follows_batch_size(evg, cfg, monkeypatch):
+    """evg_create picks the warp-per-match kernel for small batches and the thread-per-match kernel for large ones;
+    scripted agents work with both (rows passed through the action buffer next to the warp kernel)."""
+    monkeypatch.delenv("EVG_STEP_KERNEL", raising=False)
+    small = evg.BatchedEvergladesEnv(256, seed=1, config=cfg)
+    large = evg.BatchedEvergladesEnv(16384, seed=1, config=cfg)
+    assert small._lib.evg_step_kernel_kind(small._h) == 0
+    assert large._lib.evg_step_kernel_kind(large._h) == 1
+    small.reset()
+    large.reset()
+    for _ in range(40):
+        so, sr, sd, _ = small.step_agents()
+        lo, lr, ld, _ = large.step_agents()
+    assert bool((so == lo[:256]).all()) and bool((sr == lr[:256]).all()) and bool((sd == ld[:256]).all())
