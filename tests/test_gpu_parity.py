@@ -372,3 +372,39 @@ def test_step_kernel_kind_follows_batch_size(evg, cfg, monkeypatch):
         so, sr, sd, _ = small.step_agents()
         lo, lr, ld, _ = large.step_agents()
     assert bool((so == lo[:256]).all()) and bool((sr == lr[:256]).all()) and bool((sd == ld[:256]).all())
+
+
+@pytest.mark.parametrize("kind", ["dqn", "ppo"])
+def test_policy_in_the_loop_rollout_matches_oracle(evg, eo, cfg, kind):
+    """BASELINE config 3 in small: a torch network of the reference's shape reads the observation tensor the step
+    kernel wrote (in place), its outputs are decoded on the device (DQNAgent.filter_actions / PPO's unravel) and fed
+    back into the step.  The oracle replays the same decoded rows: the whole chain stays on the reference's rules."""
+    import importlib.util, os, torch
+    spec = importlib.util.spec_from_file_location("policy_rollout", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                               "tools", "policy_rollout.py"))
+    pr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pr)
+    n = 384
+    cfg.auto_reset = 2
+    cfg.turn_limit = 50
+    try:
+        env = evg.BatchedEvergladesEnv(n, seed=5, config=cfg, auto_reset=2, env_id_offset=40)
+        ora = eo.OracleBatch(cfg, n, seed=5, first=40)
+        net = pr.build_policy(kind, torch.float32, env.device, seed=3)
+        assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
+        torch.manual_seed(11)
+        moved = 0
+        for t in range(120):
+            assert env.obs.view(-1, env.obs_len).data_ptr() == env.obs.data_ptr()  # consumed in place
+            acts = pr.policy_actions(env, net, kind, torch.float32).cpu().numpy().copy()
+            obs, rew, done, info = env.step(acts)
+            oobs, orew, odone = ora.step(acts)
+            assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+            assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
+            assert np.array_equal(done.cpu().numpy(), odone), t
+            moved += int((obs[:, :, 48::5] != 0).sum())
+        assert moved > 0  # the policies do get groups under way
+        assert_states_equal(env.get_state(), ora.states, "end")
+    finally:
+        cfg.auto_reset = 0
+        cfg.turn_limit = 150

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3]: PyTorch policy-in-the-loop self-play rollout.
+
+    python tools/policy_rollout.py [--envs-per-gpu 32768] [--turns 300] [--policy dqn|ppo] [--dtype fp32|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/policy_rollout.py
+
+Both players are driven by one network of the reference's shape — DQN: Linear(105, 528) - ReLU - Linear(528, 132)
+(agents/DQN/QNetwork.py:37-42, random weights), decoded like DQNAgent.filter_actions (evg_decode_dqn); PPO: the
+actor's Linear(105, 128) - Tanh - Linear(128, 128) - Tanh - Linear(128, 132) - Tanh - Softmax head
+(agents/PPO/ActorCritic.py:33-50, without the GRU), 7 indices sampled without replacement and unravelled like
+PPOAgent.get_action (evg_decode_indices).  The observation tensor the step kernel writes is consumed in place
+(a [N*2, 105] view, no copy, no dtype conversion kernel for fp32); the decoded int8 rows go straight back into the
+step.  Matches shard over the ranks with no collective on the path; rank 0 prints one JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import evgsim
+
+
+def build_policy(kind, dtype, device, seed=0):
+    torch.manual_seed(seed)
+    if kind == "dqn":
+        net = torch.nn.Sequential(torch.nn.Linear(105, 528), torch.nn.ReLU(), torch.nn.Linear(528, 132))
+    else:
+        net = torch.nn.Sequential(torch.nn.Linear(105, 128), torch.nn.Tanh(), torch.nn.Linear(128, 128), torch.nn.Tanh(),
+                                  torch.nn.Linear(128, 132), torch.nn.Tanh(), torch.nn.Softmax(dim=-1))
+    return net.to(device=device, dtype=dtype).eval()
+
+
+@torch.no_grad()
+def policy_actions(env, net, kind, dtype):
+    x = env.obs.view(-1, env.obs_len)  # [N*2, 105], the step kernel's output buffer itself
+    out = net(x if dtype == torch.float32 else x.to(dtype))
+    if kind == "dqn":
+        return env.decode_dqn(out.float().view(env.num_envs, 2, -1))
+    idx = torch.multinomial(out.float(), 7, replacement=False)  # PPOAgent.get_action draws 7 distinct flat indices
+    return env.decode_indices(idx.view(env.num_envs, 2, 7), div=12, mod=11)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs-per-gpu", type=int, default=32768)  # 262,144 over 8 GPUs
+    ap.add_argument("--turns", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=150)
+    ap.add_argument("--policy", default="dqn", choices=["dqn", "ppo"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    E = args.envs_per_gpu
+    first, _ = evgsim.shard_range(E * world, rank, world)
+    env = evgsim.BatchedEvergladesEnv(E, device=local, seed=0, auto_reset=evgsim._capi.AUTORESET_TERMINAL, env_id_offset=first)
+    net = build_policy(args.policy, dtype, env.device)
+    env.reset()
+    for _ in range(args.warmup):
+        env.step(policy_actions(env, net, args.policy, dtype))
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.turns):
+        env.step(policy_actions(env, net, args.policy, dtype))
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=env.device)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    stats = evgsim.gather_episode_stats(env.episode_stats(), device=env.device) if world > 1 else env.episode_stats()
+    if rank == 0:
+        sec = float(ms.item()) / 1e3
+        print(json.dumps({"workload": "policy-in-the-loop self-play (BASELINE.json configs[3])", "policy": args.policy, "dtype": args.dtype,
+                          "n_gpus": world, "envs_per_gpu": E, "turns": args.turns, "env_turns_per_s": E * world * args.turns / sec,
+                          "ms_per_turn": sec * 1e3 / args.turns, "episodes": stats["episodes"], "wins": stats["wins"], "ties": stats["ties"]}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
