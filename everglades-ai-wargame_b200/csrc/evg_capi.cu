@@ -145,6 +145,13 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
         if (dmg_sum > max_dmg_sum) max_dmg_sum = dmg_sum;
     }
     for (int g = 0; g < EVG_NUM_GROUPS; ++g) t.g_slot[EVG_NUM_GROUPS + g] = (uint16_t)(t.g_slot[EVG_NUM_GROUPS + g] + per_player_slots);
+    for (int L = 0; L < evg::kGroupLanes; ++L) {
+        t.g_move[L] = (uint32_t)t.g_speed[L] | (uint32_t)t.g_control[L] << 8 | (uint32_t)t.g_cost[L] << 16;
+        t.g_fight[L] = (uint32_t)t.g_slot[L] | (uint32_t)t.g_size[L] << 12 | (uint32_t)t.g_damage[L] << 17 | (uint32_t)t.g_type[L] << 25;
+    }
+    if (c.n_nodes <= 15)
+        for (int n = 0; n <= c.n_nodes; ++n) t.p1_nib |= (uint64_t)(t.p1_map[n] & 15u) << (4 * n);
+    for (int n = 1; n <= c.n_nodes; ++n) t.node_cap[n] = ((uint32_t)t.node_cp[n] & 0xFFFFu) | (uint32_t)(t.node_team_start[n] + 1) << 16;
     t.health_slots = 2 * per_player_slots;
     t.max_group_size = max_size;
     t.has_small_groups = small;

@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
 
     const Geo<NODES> G(S);
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
+    // player 1's node numbering (server.py:89): two registers of nibbles on the compile-time map, the byte table otherwise
+    const uint64_t p1n = S.p1_nib;
+    auto p1map = [&](uint32_t i) -> uint32_t { return NODES ? (uint32_t)(p1n >> (4 * i)) & 15u : (uint32_t)S.p1_map[i]; };
     // the observation entries that never change (a third of them: the nodes' DEFENSE/OBSERVE flags in each viewer's
     // numbering and the groups' unit types) are converted once per CTA; packing copies them from here
     float* oconst = reinterpret_cast<float*>(smem + T.sm_tables_bytes);
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 const int pl = r >= EVG_MAX_ACTIONS ? 1 : 0;
                 const bool okg = (unsigned)ag < (unsigned)EVG_NUM_GROUPS;
                 an = (unsigned)an <= (unsigned)n_nodes ? an : 0;
-                if (pl) an = S.p1_map[an];  // server.py:233-234
+                if (pl) an = (int)p1map((uint32_t)an);  // server.py:233-234
                 const int L = pl * EVG_NUM_GROUPS + (okg ? ag : 0);
                 const uint32_t gw0 = R[2 * L];
                 const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             uint32_t* Rm = wrow + (size_t)m * P;
             const uint32_t* Xm = wx + m;
             int L = 0, side = 0, x = 1, tb = 0;
-            uint32_t w0 = 0, w1 = 0;
+            uint32_t w0 = 0, w1 = 0, gf = 0;
             double hv[MAXSZ];
             double* hp = A.health;
             const int nf = __popc(fmm);
@@ -398,9 +401,10 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             __syncwarp();  // pool zeroed
             if (act) {
                 L = extra ? kth_set_bit(xmm, q - pm - nf) : kth_set_bit(fmm, q - pm);
+                gf = S.g_fight[L];  // health slot | unit slots << 12 | damage << 17 | unit type << 25
                 if (!extra) {
-                    hp = A.health + (warp_env0 + m) * S.health_slots + S.g_slot[L];
-                    load_group<MAXSZ>(hp, S.g_size[L], hv);  // consumed after the draws
+                    hp = A.health + (warp_env0 + m) * S.health_slots + (gf & 0xFFFu);
+                    load_group<MAXSZ>(hp, (int)((gf >> 12) & 31u), hv);  // consumed after the draws
                 }
                 side = L >= EVG_NUM_GROUPS ? 1 : 0;
                 const int gg = L - side * EVG_NUM_GROUPS;
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 // This item draws for units [8 * jb, 8 * jb + nd)
                 const uint32_t jb = extra ? 1u : 0u;
                 const uint32_t nd = extra ? cnt - 8u : (((xmm >> L) & 1u) ? 8u : cnt);
-                const uint32_t dmg = S.g_damage[L];
+                const uint32_t dmg = (gf >> 17) & 0xFFu;
                 const uint32_t turn_m = Rm[kRecTurn] + 1u, ep_m = Rm[kRecEpisode];
                 for (uint32_t b = jb; 8u * (b - jb) < nd; ++b) {
                     uint32_t r[4];
@@ -450,14 +454,14 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 const uint32_t nwd = Rm[kRecNode0 + x - 1];
                 const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
                 const int bonus = (cb == side ? 1 : 0) + ((S.node_flags[x] >> 2) & 1);
-                const int type = S.g_type[L];
+                const int type = (int)(gf >> 25);
                 const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const int ti = (type * nn + x) * 3 + bonus;
                 constexpr bool FMA_ONLY = NODES != 0;  // the compile-time map's kernel is only picked when Tables::fast_div holds
                 const double* ltab = FMA_ONLY || S.fast_div ? nullptr : S.loss_tab + (size_t)ti * kLossD;
                 const double rcp = FMA_ONLY || S.fast_div ? __ldg(S.rcp_tab + ti) : 0.0;
                 int avg;
-                const uint32_t alive = apply_group<MAXSZ, HistT, FMA_ONLY>(hp, hv, S.g_size[L], w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
+                const uint32_t alive = apply_group<MAXSZ, HistT, FMA_ONLY>(hp, hv, (int)((gf >> 12) & 31u), w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
                                                                            tb, ltab, divisor, &avg, rcp);
                 Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
                 Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
@@ -487,7 +491,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 const uint32_t w0 = w.x, alive = w.y & 0xFFFFu;
                 const bool live = alive != 0;  // destroyed groups are skipped, :663
                 const bool rdy = (w0 & W0_READY) != 0, mov = (w0 & W0_MOVING) != 0;
-                const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)S.g_speed[L];  // :671
+                const uint32_t gm = S.g_move[L];  // speed | control << 8 | cost << 16
+                const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)(gm & 0xFFu);  // :671
                 const bool arrive = live && !rdy && mov && dist <= 0;
                 const uint32_t w_rdy = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
                 const uint32_t w_arr = (w0 & (127u << W0_AVG_SHIFT)) | ((w0 >> W0_DEST_SHIFT) & 0x3Fu);  // appended to the destination's list (:678-695)
@@ -497,10 +502,10 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 R[2 * L] = n0;
                 if (arrive) R[2 * L + 1] = alive | turn << 16;
                 const uint32_t cnt = __popc(alive);
-                const uint32_t hold = (n0 & W0_MOVING) ? 0u : ((cnt * S.g_control[L]) << 10 | 1u << 24);
+                const uint32_t hold = (n0 & W0_MOVING) ? 0u : ((cnt * ((gm >> 8) & 0xFFu)) << 10 | 1u << 24);
                 v = live ? (cnt | hold) : 0u;
                 loc = live ? (n0 & W0_LOC_MASK) : 0u;
-                pts = (int)cnt * (int)S.g_cost[L];
+                pts = (int)(cnt * (gm >> 16));
                 any_alive |= live;
             };
 #pragma unroll kMoveUnroll
@@ -524,7 +529,8 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             int cs = (int)(int16_t)(nw & 0xFFFFu), cb = (int)(int8_t)((nw >> 16) & 0xFFu);
             const uint32_t a0 = X[32 * n], a1 = X[32 * (nn + n)];
             const bool c0 = (a0 >> 24) != 0, c1 = (a1 >> 24) != 0;
-            const int cp = S.node_cp[n];
+            const uint32_t ncap = S.node_cap[n];  // control points | (TeamStart + 1) << 16
+            const int cp = (int)(ncap & 0xFFFFu);
             const int pid = c1 ? 1 : 0;
             const bool upd = c0 != c1 && (abs(cs) < cp || pid != cb);  // exactly one controller (:729), :731-732
             {
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
                 cb = upd ? cb2 : cb;
                 if (upd) R[kRecNode0 + n - 1] = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
             }
-            const int ts = S.node_team_start[n];
+            const int ts = (int)(ncap >> 16) - 1;
             const bool bc = ts != -1 && cb != -1 && cb != ts;
             basecap |= bc;
             const int bonus = bc ? S.capture_bonus : 0;
@@ -596,7 +602,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             if (i == 0) return (float)turn;
             if (i < 1 + 4 * n_nodes) {
                 const int k = (i - 1) >> 2, j = (i - 1) & 3;
-                const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
+                const int x = p ? (int)p1map((uint32_t)(k + 1)) : k + 1;  // server.py:437-439
                 if (j < 2) return oconst[f];  // 'DEFENSE' / 'OBSERVE' in resource, :442-443
                 if (j == 2) return (float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu);  // raw sign for both viewers
                 return (float)(X[32 * ((p ? 0 : nn) + x)] & 1023u);                                  // opposing listed units
@@ -604,7 +610,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
             const int q = i - 1 - 4 * n_nodes, g = q / 5, j = q - 5 * g;
             const int L = p * EVG_NUM_GROUPS + g;
             const uint32_t w0 = R[2 * L];
-            if (j == 0) return (float)(p ? (uint32_t)S.p1_map[w0 & W0_LOC_MASK] : (w0 & W0_LOC_MASK));
+            if (j == 0) return (float)(p ? p1map(w0 & W0_LOC_MASK) : (w0 & W0_LOC_MASK));
             if (j == 1) return oconst[f];  // unit type id
             if (j == 2) return (float)((w0 >> W0_AVG_SHIFT) & 127u);
             if (j == 3) return (float)((w0 >> 21) & 1u);
