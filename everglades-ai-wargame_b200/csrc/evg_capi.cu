@@ -12,6 +12,10 @@
 
 #include "evg_internal.h"
 
+#ifndef EVG_TPM_SMALL_MAX_DEFAULT
+#define EVG_TPM_SMALL_MAX_DEFAULT 65536  // matches up to which the one-warp-per-CTA instantiation is used (env EVG_TPM_SMALL_MAX)
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -56,7 +60,8 @@ struct EvgSim {
     bool use_pair;    // two lanes per match (EVG_STEP_KERNEL=pair) instead of one thread per match (=tpm)
     const uint4* tables_dev;  // Tables in device memory (inside bind slot EVG_BIND_TABLES)
     size_t tpm_smem;
-    int tpm_grid;  // persistent CTAs: SMs x resident CTAs
+    int tpm_grid;     // persistent CTAs: SMs x resident CTAs
+    int tpm_threads;  // 128, or 32 (one warp per CTA) for small batches
     size_t pair_smem;
     int pair_grid;
 };
@@ -338,8 +343,15 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     int pair_per_sm = 0;
     if ((e = evg::pair_prepare(t, &s->pair_smem, &pair_per_sm)) != cudaSuccess || pair_per_sm < 1) { delete s; return cuda_fail(e, "lane-pair kernel setup"); }
     s->pair_grid = prop.multiProcessorCount * pair_per_sm;
+    // mid-size batches: one warp per CTA spreads the warps over all SMs (measured: +9 % at 65,536 matches, +5 % at
+    // 32,768, slower from 98,304 on where the 128-thread CTAs' shared instruction stream wins; profiles/README.md)
+    {
+        const char* small = getenv("EVG_TPM_SMALL_MAX");
+        const int64_t small_max = small ? atoll(small) : EVG_TPM_SMALL_MAX_DEFAULT;
+        s->tpm_threads = evg::tpm_has_small(t) && n_envs <= small_max ? evg::kTpmSmallThreads : evg::kTpmThreads;
+    }
     int tpm_per_sm = 0;
-    if ((e = evg::tpm_prepare(t, &s->tpm_smem, &tpm_per_sm)) != cudaSuccess || tpm_per_sm < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
+    if ((e = evg::tpm_prepare(t, s->tpm_threads, &s->tpm_smem, &tpm_per_sm)) != cudaSuccess || tpm_per_sm < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
     s->tpm_grid = prop.multiProcessorCount * tpm_per_sm;
     if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
     int per_sm = 0;
@@ -460,7 +472,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.tables_dev = sim->tables_dev;
     cudaError_t e = !sim->use_tpm  ? evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream)
                     : sim->use_pair ? evg::launch_step_pair(sim->tables, a, sim->pair_smem, sim->pair_grid, (cudaStream_t)stream)
-                                    : evg::launch_step_tpm(sim->tables, a, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
+                                    : evg::launch_step_tpm(sim->tables, a, sim->tpm_threads, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;
     sim->steps += 1;

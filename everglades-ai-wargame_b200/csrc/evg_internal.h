@@ -87,6 +87,7 @@ constexpr int kAgentMaxNodes = 15;  // nibble-packed node permutation of the on-
 #define EVG_TPM_THREADS 128
 #endif
 constexpr int kTpmThreads = EVG_TPM_THREADS;
+constexpr int kTpmSmallThreads = 32;  // the one-warp-per-CTA instantiation for small batches (compile-time map only)
 #ifndef EVG_TPM_STAGE
 #define EVG_TPM_STAGE 32
 #endif
@@ -139,8 +140,9 @@ cudaError_t launch_agents(const Tables& t, const uint32_t* records, uint2* agent
 cudaError_t step_occupancy(const Tables& t, size_t smem, int* blocks_per_sm);
 cudaError_t set_step_smem(size_t smem);
 // thread-per-match step (evg_step_tpm.cu)
-cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm);
-cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream);
+bool tpm_has_small(const Tables& t);
+cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blocks_per_sm);
+cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, size_t smem, int max_grid, cudaStream_t stream);
 // two lanes per match (evg_step_pair.cu)
 cudaError_t pair_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm);
 cudaError_t launch_step_pair(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream);

@@ -132,15 +132,17 @@ __device__ __noinline__ void load_rows_direct(const StepArgs& A, uint32_t* wrow,
 
 // AGENTS: the instantiation that can generate scripted players' rows itself (evg_step_agents); the plain step
 // leaves that code out, the kernel's instruction footprint being what its instruction cache misses are made of
-template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS>
-__global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
+// THREADS: 128 (a CTA = 4 warps sharing tables, barrier and instruction stream), or 32 for small batches: one warp
+// per CTA spreads a few thousand matches over all SMs instead of a fifth of them.
+template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_CTAS : 1) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // chunk of a 512-byte pair of records a lane moves in the whole-warp copies: lane bits 3 and 4 swapped, so that a
     // half-warp covers chunks 0..7 (or 8..15) of BOTH records and its 8-byte row accesses fall into 16 different bank pairs
     const int pl = (lane & 7) | ((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 4;
-    const int64_t nbatches = (A.n_envs + kTpmThreads - 1) / kTpmThreads;
+    const int64_t nbatches = (A.n_envs + THREADS - 1) / THREADS;
     const bool ext_rows = A.agent[0] == EVG_AGENT_EXTERNAL || A.agent[1] == EVG_AGENT_EXTERNAL;
     // Software pipeline (compile-time map only: 16 chunks of 16 bytes per record): the NEXT batch's records and
     // action rows are requested into registers before this batch's observation phase, so their DRAM latency is
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     uint32_t nxa[7];
     bool have = false;
     auto request = [&](int64_t b) -> bool {
-        const int64_t e0 = b * kTpmThreads + warp * 32;
+        const int64_t e0 = b * THREADS + warp * 32;
         if (b >= nbatches || e0 + 32 > A.n_envs) return false;  // partial warps take the direct path
         const uint4* g4 = reinterpret_cast<const uint4*>(A.records) + e0 * 16;
 #pragma unroll
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
     // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
     // touches its own 32 rows, so batches need no CTA-wide barrier
     for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
-    const int64_t warp_env0 = batch * kTpmThreads + warp * 32;
+    const int64_t warp_env0 = batch * THREADS + warp * 32;
     const int64_t env = warp_env0 + lane;
     const int64_t left = A.n_envs - warp_env0;
     const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kTpmThreads, EVG_TPM_MIN_CTAS) evg_step_tpm_ke
         // (action rows requested before the records so the latencies overlap)
 #pragma unroll
         for (int k = 0; k < 7; ++k) aw[k] = (valid && ext_rows) ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
-        load_rows_direct<NODES>(A, wrow, P, RW, RWU, warp_env0, nvalid, lane, !PIPE, warp_env0 + (int64_t)gridDim.x * kTpmThreads);
+        load_rows_direct<NODES>(A, wrow, P, RW, RWU, warp_env0, nvalid, lane, !PIPE, warp_env0 + (int64_t)gridDim.x * THREADS);
     }
     __syncwarp();
     EVG_PHASE_SYNC(0);
@@ -706,42 +708,54 @@ Variant pick(const Tables& t)
 
 }  // namespace
 
-cudaError_t tpm_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
+bool tpm_has_small(const Tables& t) { return pick(t) == V_FAST; }
+
+cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blocks_per_sm)
 {
     size_t smem = (size_t)t.sm_tables_bytes + (size_t)((2 * t.obs_len * 4 + 15) & ~15) +
-                  (size_t)(kTpmThreads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
+                  (size_t)(threads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
     cudaError_t e;
-#define EVG_TPM_EACH(F)                                         \
-    F((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false>)) \
-    F((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true>))  \
-    F((evg_step_tpm_kernel<0, 16, uint8_t, 0, true>))            \
-    F((evg_step_tpm_kernel<0, 16, uint16_t, 0, true>))
 #define EVG_TPM_ATTR(K) \
     if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    EVG_TPM_EACH(EVG_TPM_ATTR)
+    if (threads == kTpmSmallThreads) {
+        if (pick(t) != V_FAST) return cudaErrorInvalidValue;
+        EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads>))
+        EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads>))
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads>,
+                                                             threads, smem);
+    }
+    EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmThreads>))
+    EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmThreads>))
+    EVG_TPM_ATTR((evg_step_tpm_kernel<0, 16, uint8_t, 0, true, kTpmThreads>))
+    EVG_TPM_ATTR((evg_step_tpm_kernel<0, 16, uint16_t, 0, true, kTpmThreads>))
 #undef EVG_TPM_ATTR
     switch (pick(t)) {
-        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false>, kTpmThreads, smem); break;
-        case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint8_t, 0, true>, kTpmThreads, smem); break;
-        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint16_t, 0, true>, kTpmThreads, smem); break;
+        case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmThreads>, kTpmThreads, smem); break;
+        case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint8_t, 0, true, kTpmThreads>, kTpmThreads, smem); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<0, 16, uint16_t, 0, true, kTpmThreads>, kTpmThreads, smem); break;
     }
     return e;
 }
 
-cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream)
+cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, size_t smem, int max_grid, cudaStream_t stream)
 {
-    const int64_t nb = (a.n_envs + kTpmThreads - 1) / kTpmThreads;
+    const int64_t nb = (a.n_envs + threads - 1) / threads;
     const unsigned grid = (unsigned)(nb < max_grid ? nb : max_grid);
     const bool agents = a.agent[0] != EVG_AGENT_EXTERNAL || a.agent[1] != EVG_AGENT_EXTERNAL;
+    if (threads == kTpmSmallThreads) {
+        if (agents) evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads><<<grid, threads, smem, stream>>>(t, a);
+        else evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads><<<grid, threads, smem, stream>>>(t, a);
+        return cudaGetLastError();
+    }
     switch (pick(t)) {
         case V_FAST:
-            if (agents) evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true><<<grid, kTpmThreads, smem, stream>>>(t, a);
-            else evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false><<<grid, kTpmThreads, smem, stream>>>(t, a);
+            if (agents) evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a);
+            else evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a);
             break;
-        case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0, true><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
-        default: evg_step_tpm_kernel<0, 16, uint16_t, 0, true><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0, true, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
+        default: evg_step_tpm_kernel<0, 16, uint16_t, 0, true, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
     }
     return cudaGetLastError();
 }

@@ -252,10 +252,14 @@ def test_step_host_equals_step(evg, eo, cfg):
     assert env.h2d_bytes_per_step() == n * 28 and env.d2h_bytes_per_step() == n * (840 + 8 + 1)
 
 
-@pytest.mark.parametrize("kernel", ["pair", "tpm", "warp"])
+@pytest.mark.parametrize("kernel", ["pair", "tpm", "tpm128", "warp"])
 def test_every_step_kernel_matches_oracle(evg, eo, cfg, monkeypatch, kernel):
-    """The three step kernels (two lanes per match / one thread per match / one warp per match) stay selectable
-    (EVG_STEP_KERNEL) for A/B profiling; each must match the oracle, with auto-reset and a tail batch (n % 128 != 0)."""
+    """The step kernels (two lanes per match / one thread per match in 32- and in 128-thread CTAs / one warp per match)
+    stay selectable (EVG_STEP_KERNEL, EVG_TPM_SMALL_MAX) for A/B profiling; each must match the oracle, with auto-reset
+    and a tail batch (n % 128 != 0)."""
+    if kernel == "tpm128":
+        monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")  # batches this small would take the one-warp-per-CTA instantiation
+        kernel = "tpm"
     monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
     rng = np.random.default_rng(31)
     cfg.turn_limit = 70
@@ -267,8 +271,14 @@ def test_every_step_kernel_matches_oracle(evg, eo, cfg, monkeypatch, kernel):
         cfg.auto_reset = 0
 
 
-def test_fused_agents_equal_agent_kernel_plus_step(evg, eo, cfg):
-    """evg_step_agents (rows generated inside the step kernel) == evg_agent_random + evg_step == oracle."""
+@pytest.mark.parametrize("kernel", ["default", "tpm", "tpm128"])
+def test_fused_agents_equal_agent_kernel_plus_step(evg, eo, cfg, monkeypatch, kernel):
+    """evg_step_agents (rows generated inside the step kernel) == evg_agent_random + evg_step == oracle, for the
+    batch-size default (warp kernel: rows through the action buffer) and both thread-per-match CTA sizes (fused)."""
+    if kernel != "default":
+        monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
+        if kernel == "tpm128":
+            monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")
     n = 640
     cfg.auto_reset = 1
     cfg.turn_limit = 60
@@ -351,6 +361,7 @@ def test_loss_quotient_paths_agree(evg, eo, cfg, monkeypatch):
     equal to the IEEE quotient for every reachable dmg (Tables::fast_div); EVG_NO_FAST_DIV forces the generic
     instantiation with the loss table / division.  Both must reproduce the oracle's fp64 health bit for bit."""
     monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
+    monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")
     rng = np.random.default_rng(77)
     for no_fast in ("", "1"):
         if no_fast:
