@@ -133,6 +133,21 @@ def test_oracle_parity_4096_adjacent_random(evg, eo, cfg):
     run_against_oracle(evg, eo, cfg, 4096, 150, seed=11, first=0, make_actions=lambda s: adjacent_actions(rng, s, cfg))
 
 
+def test_oracle_parity_16384_default_kernel_choice(evg, eo, cfg, monkeypatch):
+    """A mid-size batch takes the thread-per-match kernel with one warp per CTA by default (evg_create's choice): every
+    one of the 16,384 matches is followed on the oracle through a full episode with in-place auto-reset."""
+    monkeypatch.delenv("EVG_STEP_KERNEL", raising=False)
+    monkeypatch.delenv("EVG_TPM_SMALL_MAX", raising=False)
+    rng = np.random.default_rng(5)
+    try:
+        env, ora, ndone = run_against_oracle(evg, eo, cfg, 16384, 155, seed=41, first=1 << 21,
+                                             make_actions=lambda s: adjacent_actions(rng, s, cfg), auto_reset=1, state_every=31)
+        assert env._lib.evg_step_kernel_kind(env._h) == 1
+        assert ndone >= 16384
+    finally:
+        cfg.auto_reset = 0
+
+
 def test_oracle_parity_uniform_random_with_offset(evg, eo, cfg):
     """random_actions-style rows (mostly invalid moves), match ids starting at a large offset."""
     rng = np.random.default_rng(2)
