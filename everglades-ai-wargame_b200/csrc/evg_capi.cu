@@ -151,7 +151,7 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     }
     for (int g = 0; g < EVG_NUM_GROUPS; ++g) t.g_slot[EVG_NUM_GROUPS + g] = (uint16_t)(t.g_slot[EVG_NUM_GROUPS + g] + per_player_slots);
     for (int L = 0; L < evg::kGroupLanes; ++L) {
-        t.g_move[L] = (uint32_t)t.g_speed[L] | (uint32_t)t.g_control[L] << 8 | (uint32_t)t.g_cost[L] << 16;
+        t.g_move[2 * (L % EVG_NUM_GROUPS) + L / EVG_NUM_GROUPS] = (uint32_t)t.g_speed[L] | (uint32_t)t.g_control[L] << 8 | (uint32_t)t.g_cost[L] << 16;
         t.g_fight[L] = (uint32_t)t.g_slot[L] | (uint32_t)t.g_size[L] << 12 | (uint32_t)t.g_damage[L] << 17 | (uint32_t)t.g_type[L] << 25;
     }
     if (c.n_nodes <= 15)

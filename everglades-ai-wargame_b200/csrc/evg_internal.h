@@ -67,9 +67,10 @@ struct alignas(16) Tables {
     // words) and a per-warp damage-histogram pool sized for one round of 32 fighting groups
     int32_t tpm_pitch, tpm_pool_words, tpm_hist16;
     uint32_t big_mask;  // group lanes (bit L) with more than 8 unit slots
-    // per group lane, one word instead of several byte tables: speed [0:8) | control [8:14) | cost [16:24);
-    // health slot [0:12) | unit slots [12:17) | damage [17:25) | unit type [25:28)
-    uint32_t g_move[kGroupLanes], g_fight[kGroupLanes];
+    // per group, one word instead of several byte tables.  g_move[2 * gid + player]: speed [0:8) | control [8:14) | cost [16:24);
+    // g_fight[lane]: health slot [0:12) | unit slots [12:17) | damage [17:25) | unit type [25:28)
+    alignas(8) uint32_t g_move[kGroupLanes];
+    uint32_t g_fight[kGroupLanes];
     uint32_t node_cap[kNN];  // control points [0:16) | (TeamStart + 1) [16:18)
     uint32_t pad_t;
     uint64_t p1_nib;  // p1_map as nibbles (node i at bits [4i, 4i+4)) for maps of <= 15 nodes: a register lookup

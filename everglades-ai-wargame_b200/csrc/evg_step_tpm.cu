@@ -179,7 +179,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     // the observation entries that never change (a third of them: the nodes' DEFENSE/OBSERVE flags in each viewer's
     // numbering and the groups' unit types) are converted once per CTA; packing copies them from here
     float* oconst = reinterpret_cast<float*>(smem + T.sm_tables_bytes);
-    const int oc_bytes = (2 * OL * 4 + 15) & ~15;
+    const int oc_floats = (2 * OL + 3) & ~3;
+    float2* ocpair = reinterpret_cast<float2*>(oconst + oc_floats);  // [player][viewer slot]: the node's two flags
+    const int oc_bytes = oc_floats * 4 + ((2 * n_nodes * 8 + 15) & ~15);
+    for (int i = threadIdx.x; i < 2 * n_nodes; i += blockDim.x) {
+        const int p = i >= n_nodes ? 1 : 0, k = i - p * n_nodes;
+        const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
+        ocpair[i] = make_float2((float)(S.node_flags[x] & 1u), (float)((S.node_flags[x] >> 1) & 1u));
+    }
     for (int f = threadIdx.x; f < 2 * OL; f += blockDim.x) {
         const int p = f >= OL ? 1 : 0, i = f - p * OL;
         float v = 0.f;
@@ -488,12 +495,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             uint32_t* __restrict__ acc1 = X + 32 * nn;
             // written with selects: the four cases (idle, ready, under way, arriving) differ per match, so branches
             // would run them one after the other
-            auto move = [&](int L, uint32_t& v, uint32_t& loc, int& pts) {
+            auto move = [&](int L, uint32_t gm, uint32_t& v, uint32_t& loc, int& pts) {
                 const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);
                 const uint32_t w0 = w.x, alive = w.y & 0xFFFFu;
                 const bool live = alive != 0;  // destroyed groups are skipped, :663
                 const bool rdy = (w0 & W0_READY) != 0, mov = (w0 & W0_MOVING) != 0;
-                const uint32_t gm = S.g_move[L];  // speed | control << 8 | cost << 16
                 const int dist = (int)((w0 >> W0_DIST_SHIFT) & 0xFFu) - (int)(gm & 0xFFu);  // :671
                 const bool arrive = live && !rdy && mov && dist <= 0;
                 const uint32_t w_rdy = (w0 & ~W0_READY) | W0_MOVING;  // first turn only flips ready -> moving (:664-667)
@@ -514,8 +520,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
                 uint32_t va, la, vb, lb;
                 int pa, pb;
-                move(g, va, la, pa);
-                move(EVG_NUM_GROUPS + g, vb, lb, pb);
+                const uint2 gm = *reinterpret_cast<const uint2*>(&S.g_move[2 * g]);  // {player 0's, player 1's}: speed | control << 8 | cost << 16
+                move(g, gm.x, va, la, pa);
+                move(EVG_NUM_GROUPS + g, gm.y, vb, lb, pb);
                 atomicAdd(&acc0[32 * la], va);  // entry 0 collects the (zero) contributions of dead groups
                 atomicAdd(&acc1[32 * lb], vb);
                 s0 += pa;
@@ -605,18 +612,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             if (i < 1 + 4 * n_nodes) {
                 const int k = (i - 1) >> 2, j = (i - 1) & 3;
                 const int x = p ? (int)p1map((uint32_t)(k + 1)) : k + 1;  // server.py:437-439
-                if (j < 2) return oconst[f];  // 'DEFENSE' / 'OBSERVE' in resource, :442-443
+                if (j < 2) {  // 'DEFENSE' / 'OBSERVE' in resource, :442-443: both flags of a node from one 8-byte load
+                    const float2 c2 = ocpair[p * n_nodes + k];
+                    return j ? c2.y : c2.x;
+                }
                 if (j == 2) return (float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu);  // raw sign for both viewers
                 return (float)(X[32 * ((p ? 0 : nn) + x)] & 1023u);                                  // opposing listed units
             }
             const int q = i - 1 - 4 * n_nodes, g = q / 5, j = q - 5 * g;
             const int L = p * EVG_NUM_GROUPS + g;
-            const uint32_t w0 = R[2 * L];
+            const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);  // one 8-byte load serves a group's five entries
+            const uint32_t w0 = w.x;
             if (j == 0) return (float)(p ? p1map(w0 & W0_LOC_MASK) : (w0 & W0_LOC_MASK));
             if (j == 1) return oconst[f];  // unit type id
             if (j == 2) return (float)((w0 >> W0_AVG_SHIFT) & 127u);
             if (j == 3) return (float)((w0 >> 21) & 1u);
-            return (float)__popc(R[2 * L + 1] & 0xFFFFu);
+            return (float)__popc(w.y & 0xFFFFu);
         };
         const int sub = lane / SP, cp = lane % SP;
         const int nchunks = (npairs + SP - 1) / SP;
@@ -712,7 +723,7 @@ bool tpm_has_small(const Tables& t) { return pick(t) == V_FAST; }
 
 cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blocks_per_sm)
 {
-    size_t smem = (size_t)t.sm_tables_bytes + (size_t)((2 * t.obs_len * 4 + 15) & ~15) +
+    size_t smem = (size_t)t.sm_tables_bytes + (size_t)(((2 * t.obs_len + 3) & ~3) * 4 + ((2 * t.n_nodes * 8 + 15) & ~15)) +
                   (size_t)(threads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
