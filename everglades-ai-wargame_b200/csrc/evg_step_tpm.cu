@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
 
         // ---- capture (server.py:708-767; current_turn > 0 here) and node scoring (server.py:298-310)
         bool basecap = false;
+        const int capture_bonus = S.capture_bonus;
 #pragma unroll kCaptureUnroll
         for (int n = 1; n <= n_nodes; ++n) {
             const uint32_t nw = R[kRecNode0 + n - 1];
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             const int ts = (int)(ncap >> 16) - 1;
             const bool bc = ts != -1 && cb != -1 && cb != ts;
             basecap |= bc;
-            const int bonus = bc ? S.capture_bonus : 0;
+            const int bonus = bc ? capture_bonus : 0;
             const int npts = abs(cs) == cp ? 2 * cp : abs(cs);
             s0 += (cb ? 0 : bonus) + (cs > 0 ? npts : 0);
             s1 += (cb ? bonus : 0) + (cs < 0 ? npts : 0);
