@@ -417,8 +417,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 }
                 side = L >= EVG_NUM_GROUPS ? 1 : 0;
                 const int gg = L - side * EVG_NUM_GROUPS;
-                w0 = Rm[2 * L];
-                w1 = Rm[2 * L + 1];
+                {
+                    const uint2 w = *reinterpret_cast<const uint2*>(Rm + 2 * L);
+                    w0 = w.x;
+                    w1 = w.y;
+                }
                 x = (int)(w0 & W0_LOC_MASK);
                 const uint32_t cnt = __popc(w1 & 0xFFFFu);
                 const uint32_t own = Xm[32 * (side * nn + x)], opp = Xm[32 * ((1 - side) * nn + x)];
@@ -442,7 +445,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 const uint32_t jb = extra ? 1u : 0u;
                 const uint32_t nd = extra ? cnt - 8u : (((xmm >> L) & 1u) ? 8u : cnt);
                 const uint32_t dmg = (gf >> 17) & 0xFFu;
-                const uint32_t turn_m = Rm[kRecTurn] + 1u, ep_m = Rm[kRecEpisode];
+                const uint2 te = *reinterpret_cast<const uint2*>(Rm + kRecTurn);  // turn, episode
+                const uint32_t turn_m = te.x + 1u, ep_m = te.y;
                 for (uint32_t b = jb; 8u * (b - jb) < nd; ++b) {
                     uint32_t r[4];
                     philox4x32_10(S.env_base + (uint32_t)(warp_env0 + m), turn_m,
@@ -472,8 +476,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 int avg;
                 const uint32_t alive = apply_group<MAXSZ, HistT, FMA_ONLY>(hp, hv, (int)((gf >> 12) & 31u), w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
                                                                            tb, ltab, divisor, &avg, rcp);
-                Rm[2 * L + 1] = (w1 & 0xFFFF0000u) | alive;  // alive == 0: destroyed, leaves the node list (:623-627)
-                Rm[2 * L] = (w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
+                // alive == 0: destroyed, leaves the node list (:623-627)
+                *reinterpret_cast<uint2*>(Rm + 2 * L) = make_uint2((w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT,
+                                                                   (w1 & 0xFFFF0000u) | alive);
             }
             __syncwarp();
             m_begin = m_end;
