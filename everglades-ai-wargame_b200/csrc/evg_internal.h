@@ -122,6 +122,17 @@ struct StepArgs {
     const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
 };
 
+// Kernels that need more than 48 KB of dynamic shared memory are opted in up to the DEVICE limit, not up to what one
+// simulator needs: the attribute is per function, and simulators of different configurations share the functions.
+inline cudaError_t optin_smem_limit(size_t needed, int* limit)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess && needed > (size_t)*limit) e = cudaErrorInvalidValue;
+    return e;
+}
+
 // launchers (evg_kernels.cu); all asynchronous on `stream`, return the launch error
 cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, float* obs,

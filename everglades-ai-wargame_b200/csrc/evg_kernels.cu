@@ -837,10 +837,13 @@ constexpr int kFastNodes = 11;
 
 cudaError_t set_step_smem(size_t smem)
 {
-    cudaError_t e = cudaFuncSetAttribute(evg_step_kernel<kFastNodes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int limit = 0;
+    cudaError_t e = optin_smem_limit(smem, &limit);
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(evg_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(evg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(evg_step_kernel<kFastNodes>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(evg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t step_occupancy(const Tables& t, size_t smem, int* blocks_per_sm)

@@ -493,9 +493,11 @@ cudaError_t pair_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm)
     const size_t smem = (size_t)t.sm_tables_bytes + 128 + (size_t)kPairMatches * t.pair_pitch * 4;
     *smem_out = smem;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<11, 12, uint8_t, 138>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    int limit = 0;
+    if ((e = optin_smem_limit(smem, &limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<11, 12, uint8_t, 138>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<0, 16, uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_step_pair_kernel<0, 16, uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
     switch (pick(t)) {
         case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_pair_kernel<11, 12, uint8_t, 138>, kPairThreads, smem); break;
         case V_GENERIC8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_pair_kernel<0, 16, uint8_t, 0>, kPairThreads, smem); break;

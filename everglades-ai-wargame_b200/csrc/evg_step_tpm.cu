@@ -734,8 +734,10 @@ cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blo
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     *smem_out = smem;
     cudaError_t e;
+    int limit = 0;
+    if ((e = optin_smem_limit(smem, &limit)) != cudaSuccess) return e;
 #define EVG_TPM_ATTR(K) \
-    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
     if (threads == kTpmSmallThreads) {
         if (pick(t) != V_FAST) return cudaErrorInvalidValue;
         EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads>))

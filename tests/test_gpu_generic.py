@@ -112,3 +112,35 @@ def test_largest_map_32_nodes(tmp_path, kernel, monkeypatch):
         assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
     assert_states_equal(env.get_state(), ora.states, "end")
     assert env.episode_stats()["episodes"] >= 2 * n
+
+
+@pytest.mark.parametrize("kernel", ["tpm", "pair", "warp"])
+def test_simulators_of_different_configurations_coexist(tmp_path, kernel, monkeypatch):
+    """The step kernels are shared by every simulator of a process; one that needs less shared memory, created
+    later, must not take the opt-in away from an earlier one that needs more (32-node map vs 7-node map vs DemoMap)."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+    from oracle import evg_oracle as eo
+
+    d32 = write_ring32(tmp_path)
+    big_cfg = evgsim.load_config(d32, "Ring32.json", evgsim.DEFAULT_CONFIG_DIR + "/UnitDefinitions.json", "Setup.json")
+    n = 200
+    big = evgsim.BatchedEvergladesEnv(n, seed=4, config=big_cfg)
+    big_ora = eo.OracleBatch(big_cfg, n, seed=4, first=0)
+    big.reset()
+    big_ora.reset()
+    small_cfg = evgsim.load_config()  # DemoMap: the smallest rows
+    small = evgsim.BatchedEvergladesEnv(n, seed=4, config=small_cfg)
+    small_ora = eo.OracleBatch(small_cfg, n, seed=4, first=0)
+    small.reset()
+    small_ora.reset()
+    rng = np.random.default_rng(8)
+    for t in range(40):
+        for env, ora, cfg in ((big, big_ora, big_cfg), (small, small_ora, small_cfg)):
+            acts = adjacent_actions(rng, ora.states, cfg)
+            obs, rew, done, info = env.step(acts)
+            oobs, orew, odone = ora.step(acts)
+            assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+            assert np.array_equal(done.cpu().numpy(), odone), t
