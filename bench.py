@@ -282,6 +282,8 @@ def main():
         dist.barrier()
     clk = clocks.stop()
     launches = env.launch_count - launches0
+    step_kernel_name = {0: "evg_step_kernel (warp per match)", 1: "evg_step_tpm_kernel (thread per match)",
+                        2: "evg_step_pair_kernel (lane pair per match)"}.get(env._lib.evg_step_kernel_kind(env._h), "?")
     total_ms = t_begin.elapsed_time(t_end)
     step_kernel_ms = sum(a.elapsed_time(b) for a, b in ev) / K
 
@@ -329,7 +331,7 @@ def main():
                     "d2h_bytes_per_step": env.d2h_bytes_per_step() * world, "steps": Ke, "ms_per_step": e2e_ms / Ke,
                     "api": "BatchedEvergladesEnv.step_host (evg_step_host), pinned host buffers"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "evg_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": step_kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(E), "peak_source": peak_src,
                          "bytes_per_env_turn": B_ALG, "kernel_ms": step_kernel_ms,
                          "kernel_env_turns_per_s": E / (step_kernel_ms / 1e3)},
