@@ -59,6 +59,9 @@ struct EvgSim {
     bool use_tpm;     // a row-based step kernel (tpm / pair) or the warp-per-match one (EVG_STEP_KERNEL=warp)
     bool use_pair;    // two lanes per match (EVG_STEP_KERNEL=pair) instead of one thread per match (=tpm)
     const uint4* tables_dev;  // Tables in device memory (inside bind slot EVG_BIND_TABLES)
+    // evg_step_host's chunk pipeline: two streams of the library's own, created on first use
+    cudaStream_t host_stream[2] = {nullptr, nullptr};
+    cudaEvent_t host_start = nullptr, host_done[2] = {nullptr, nullptr};
     size_t tpm_smem;
     int tpm_grid;     // persistent CTAs: SMs x resident CTAs
     int tpm_threads;  // 128, or 32 (one warp per CTA) for small batches
@@ -379,6 +382,15 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
 int evg_destroy(EvgSim* sim)
 {
     if (!sim) return fail(EVG_E_ARG, "null EvgSim handle");
+    if (sim->host_start) {
+        cudaSetDevice(sim->device);
+        for (int i = 0; i < 2; ++i) {
+            cudaStreamSynchronize(sim->host_stream[i]);
+            cudaStreamDestroy(sim->host_stream[i]);
+            cudaEventDestroy(sim->host_done[i]);
+        }
+        cudaEventDestroy(sim->host_start);
+    }
     delete sim;
     return EVG_OK;
 }
@@ -452,8 +464,11 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream)
     return EVG_OK;
 }
 
+// first/count: the whole batch (0, n_envs), or a 128-aligned sub-range for the thread-per-match kernel (evg_step_host's
+// chunks; all the per-match arrays are offset here, the kernel adds `first` to the global match ids)
 static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_actions, int8_t* d_actions_out, float* d_obs,
-                     float* d_reward, uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream)
+                     float* d_reward, uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream, int64_t first = 0,
+                     int64_t count = -1)
 {
     evg::StepArgs a;
     a.agent[0] = agent0;
@@ -470,12 +485,27 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
     a.tables_dev = sim->tables_dev;
+    a.env_first = 0;
+    if (count >= 0) {
+        const evg::Tables& t = sim->tables;
+        a.records += first * t.rec_words8 * 2;
+        a.health += first * t.health_slots;
+        if (a.actions) a.actions += first * 2 * EVG_MAX_ACTIONS * 2;
+        if (a.actions_out) a.actions_out += first * 2 * EVG_MAX_ACTIONS * 2;
+        a.obs += first * 2 * t.obs_len;
+        a.reward += first * 2;
+        a.done += first;
+        if (a.status) a.status += first;
+        if (a.scores) a.scores += first * 2;
+        a.n_envs = count;
+        a.env_first = first;
+    }
     cudaError_t e = !sim->use_tpm  ? evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream)
                     : sim->use_pair ? evg::launch_step_pair(sim->tables, a, sim->pair_smem, sim->pair_grid, (cudaStream_t)stream)
                                     : evg::launch_step_tpm(sim->tables, a, sim->tpm_threads, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;
-    sim->steps += 1;
+    if (count < 0 || first == 0) sim->steps += 1;
     return EVG_OK;
 }
 
@@ -522,7 +552,43 @@ int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_r
     if (!h_actions || !h_obs || !h_reward || !h_done) return fail(EVG_E_ARG, "evg_step_host: host buffers must be non-null");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = sim->n_envs;
-    cudaError_t e = cudaMemcpyAsync(d_actions, h_actions, (size_t)n * sim->layout.action_bytes, cudaMemcpyHostToDevice, st);
+    cudaError_t e;
+    // Large batches on the thread-per-match kernel go through in chunks on two streams of the library's own, so that
+    // the D2H of one chunk (the PCIe-bound part: 840 B of observations per match) overlaps the H2D and the kernel of
+    // the next; everything is ordered after what `stream` holds now and `stream` waits for all of it.
+    int chunks = 4;
+    if (const char* c = getenv("EVG_HOST_CHUNKS")) chunks = atoi(c);
+    if (chunks > 1 && sim->use_tpm && !sim->use_pair && n >= 65536) {
+        if (!sim->host_start) {
+            if ((e = cudaEventCreateWithFlags(&sim->host_start, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+            for (int i = 0; i < 2; ++i) {
+                if ((e = cudaStreamCreateWithFlags(&sim->host_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+                if ((e = cudaEventCreateWithFlags(&sim->host_done[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+            }
+        }
+        const int64_t per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+        const size_t ab = (size_t)sim->layout.action_bytes, ob = (size_t)2 * sim->layout.obs_len * 4;
+        if ((e = cudaEventRecord(sim->host_start, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+        for (int i = 0; i < 2; ++i)
+            if ((e = cudaStreamWaitEvent(sim->host_stream[i], sim->host_start, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+        int c = 0;
+        for (int64_t first = 0; first < n; first += per, ++c) {
+            const int64_t cnt = n - first < per ? n - first : per;
+            cudaStream_t cs = sim->host_stream[c & 1];
+            if ((e = cudaMemcpyAsync(d_actions + first * ab, h_actions + first * ab, (size_t)cnt * ab, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return cuda_fail(e, "H2D actions");
+            rc = step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, nullptr, nullptr, cs, first, cnt);
+            if (rc) return rc;
+            if ((e = cudaMemcpyAsync((char*)h_obs + first * ob, (const char*)d_obs + first * ob, (size_t)cnt * ob, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return cuda_fail(e, "D2H obs");
+            if ((e = cudaMemcpyAsync(h_reward + first * 2, d_reward + first * 2, (size_t)cnt * 2 * 4, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return cuda_fail(e, "D2H reward");
+            if ((e = cudaMemcpyAsync(h_done + first, d_done + first, (size_t)cnt, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return cuda_fail(e, "D2H done");
+        }
+        for (int i = 0; i < 2; ++i) {
+            if ((e = cudaEventRecord(sim->host_done[i], sim->host_stream[i])) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+            if ((e = cudaStreamWaitEvent(st, sim->host_done[i], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+        }
+        return EVG_OK;
+    }
+    e = cudaMemcpyAsync(d_actions, h_actions, (size_t)n * sim->layout.action_bytes, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "H2D actions");
     rc = evg_step(sim, d_actions, d_obs, d_reward, d_done, nullptr, nullptr, stream);
     if (rc) return rc;

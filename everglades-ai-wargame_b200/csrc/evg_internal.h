@@ -120,6 +120,8 @@ struct StepArgs {
     int32_t agent[2];      // EVG_AGENT_*: where each player's action rows come from
     int8_t* actions_out;   // optional: rows generated by scripted agents are also written here
     const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
+    int64_t env_first;        // thread-per-match kernel: this launch covers matches [env_first, env_first + n_envs) of the
+                              // simulator (all pointers above are already offset); 0 for a whole-batch launch
 };
 
 // Kernels that need more than 48 KB of dynamic shared memory are opted in up to the DEVICE limit, not up to what one

@@ -170,6 +170,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     }
     const Tables& S = *reinterpret_cast<const Tables*>(smem);
     __syncthreads();
+    if (A.env_first) {  // a sub-range launch (evg_step_host's chunks): global match ids start further on
+        if (threadIdx.x == 0) reinterpret_cast<Tables*>(smem)->env_base += (uint32_t)A.env_first;
+        __syncthreads();
+    }
 
     const Geo<NODES> G(S);
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();

@@ -434,3 +434,31 @@ def test_policy_in_the_loop_rollout_matches_oracle(evg, eo, cfg, kind):
     finally:
         cfg.auto_reset = 0
         cfg.turn_limit = 150
+
+
+def test_step_host_chunk_pipeline_equals_step(evg, eo, cfg):
+    """From 65,536 matches on evg_step_host runs the batch as four sub-range launches on two streams of its own
+    (H2D + kernel of one chunk under the D2H of the previous one).  Same results as the one-shot device-side step of a
+    twin simulator, a ragged last chunk included, and oracle parity on a sample of the matches."""
+    import torch
+    n = 70000 + 37
+    a = evg.BatchedEvergladesEnv(n, seed=21, config=cfg, env_id_offset=5)
+    b = evg.BatchedEvergladesEnv(n, seed=21, config=cfg, env_id_offset=5)
+    a.reset()
+    b.reset()
+    ids = np.unique(np.concatenate([np.arange(8), np.arange(17490, 17530), np.arange(n - 16, n)]))
+    oracles = [eo.OracleBatch(cfg, 1, seed=21, first=5 + int(i)) for i in ids]
+    for o in oracles:
+        o.reset()
+    for t in range(45):
+        acts = a.random_actions().clone()
+        obs, rew, done, _ = a.step_host(acts.cpu())
+        bobs, brew, bdone, _ = b.step(acts)
+        torch.cuda.synchronize()
+        assert bool((obs == bobs.cpu()).all()) and bool((rew == brew.cpu()).all()) and bool((done == bdone.cpu()).all()), t
+        assert bool((a.obs == bobs).all())  # the device-side copies agree too
+        host_acts = acts.cpu().numpy()
+        for i, o in zip(ids, oracles):
+            oobs, orew, odone = o.step(host_acts[i:i + 1])
+            assert np.array_equal(obs[i].numpy(), oobs[0].astype(np.float32)), (t, i)
+            assert int(done[i]) == int(odone[0]), (t, i)
