@@ -556,7 +556,7 @@ int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_r
     // Large batches on the thread-per-match kernel go through in chunks on two streams of the library's own, so that
     // the D2H of one chunk (the PCIe-bound part: 840 B of observations per match) overlaps the H2D and the kernel of
     // the next; everything is ordered after what `stream` holds now and `stream` waits for all of it.
-    int chunks = 4;
+    int chunks = 8;
     if (const char* c = getenv("EVG_HOST_CHUNKS")) chunks = atoi(c);
     if (chunks > 1 && sim->use_tpm && !sim->use_pair && n >= 65536) {
         if (!sim->host_start) {
