@@ -11,11 +11,19 @@ N = 1 — DemoMap, both players random_actions, 1,048,576 lock-step matches per 
 auto-reset; matches shard across ranks with NO collective on the step path (weak scaling; the
 only exchange is an end-of-run all_gather of episode statistics).
 
+Before anything is timed the batch is SETTLED into its steady state (--phase staggered, the default): one episode
+of untimed turns during which match i is reset after turn i mod 150, so that afterwards every phase of the game is
+present in equal shares (as it is in any long run with early terminations) and a timed window of ANY length sees the
+same mix of marching, fighting and in-place resets.  --phase lockstep keeps all matches on the same turn instead.
+
 Printed JSON (rank 0, one line): value = device-timed whole-job env-turns/s with state and inputs
 resident in HBM; e2e = the same metric through the public host-buffer API (pinned host actions
-H2D + step + D2H of observations/rewards/done flags every step); roofline = the step kernel's
-algorithmic bytes / its CUDA-event duration against the measured HBM peak; cpu_baseline = the CPU
-oracle port (oracle/evg_oracle.c) timed on this box's host cores on a bounded sample.
+H2D + step + D2H of every match's observations/rewards/done flags each step, in the packed wire
+format of include/evgsim.h by default; e2e_f32 = the same with float32 observation vectors);
+roofline = the step kernel's algorithmic bytes FOR THE TURNS THAT WERE TIMED (1331 B + 16 B per
+unit slot that fought, counted on the device) / its CUDA-event duration against the measured HBM
+peak; cpu_baseline = the unmodified Python reference (oracle/_ref, staged by oracle/stage_ref.py)
+on all host cores, with the C oracle port (oracle/evg_oracle.c) next to it.
 """
 import argparse
 import json
@@ -32,12 +40,12 @@ if ROOT not in sys.path:
 
 METRIC = "env_turns_per_sec"
 UNIT = "env-turns/s"
-# Algorithmic bytes per match-turn (SURVEY.md §8d / DESIGN.md §5): 1331 B fixed (state 227 B read +
-# written, actions 28 B, observations 840 B, rewards 8 B, done 1 B) + 16 B per unit slot of the
-# groups that fought that turn (mean 21.6 slots for random-vs-random) = 1676 B.
+# Algorithmic bytes per match-turn (SURVEY.md §8d / DESIGN.md §4.4): 1331 B fixed (state 227 B read +
+# written, actions 28 B, observations 840 B, rewards 8 B, done 1 B) + 16 B (8 read + 8 written) per unit
+# slot of the groups that fought that turn.  The slots are COUNTED ON THE DEVICE over the timed turns
+# (EvgEpisodeStats.fought_unit_slots), not assumed: a full random-vs-random episode averages 21.6.
 B_ALG_FIXED = 1331
-B_ALG_HEALTH_RANDOM = 345
-B_ALG = B_ALG_FIXED + B_ALG_HEALTH_RANDOM
+B_ALG_PER_FOUGHT_SLOT = 16
 
 
 def parse_args():
@@ -50,7 +58,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--phase", default="staggered", choices=["staggered", "lockstep"],
+                    help="staggered: settle so that match i is i mod 150 turns into its game; lockstep: all matches on the same turn")
+    ap.add_argument("--e2e-format", default="wire", choices=["wire", "i16", "f32"],
+                    help="observation transport of the headline e2e number (all lossless; f32 is always reported as e2e_f32 too)")
     ap.add_argument("--agents", default="kernel", choices=["kernel", "fused"],
                     help="random_actions rows from the agent kernel (2 launches/step) or generated inside the step kernel (1 launch)")
     return ap.parse_args()
@@ -63,6 +75,8 @@ def workload_config(args, world):
         "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
         "map": "DemoMap.json", "agents": "random_actions vs random_actions (on-device, Philox tape; %s)" % args.agents,
         "turn_limit": 150, "auto_reset": "terminal-obs", "seed": args.seed,
+        "phase": "staggered: match i is (i mod 150) turns into its game when timing starts (settled over 150 untimed turns)"
+                 if args.phase == "staggered" else "lockstep: every match on the same game turn",
         "l2": "resident state %.2f GB/GPU >> 126 MB L2; no flush between steps" % (args.envs_per_gpu * (256 + 1600) / 1e9),
         "parallelism": "match-sharded x%d, no step-path collective" % world,
     }
@@ -101,23 +115,47 @@ def cpu_oracle_rate(seconds, seed=0, threads=None, turns=150):
     return total / el, threads, sample, el
 
 
+def cpu_reference_rate(seconds):
+    """The UNMODIFIED Python reference (oracle/_ref or /root/reference) on all host cores: env-turns/s through its own
+    EvergladesEnv.reset/step.  Returns None where no copy of the reference is present."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        return None
+    rate, procs, rate_one, sample = rh.time_reference(seconds)
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample,
+            "one_process": rate_one, "source": rh.REFERENCE_ROOT}
+
+
+def cpu_baselines(seconds, seed):
+    """cpu_baseline (the real reference when a copy is present, else the port) and the port line next to it."""
+    rate, threads, sample, _ = cpu_oracle_rate(seconds, seed=seed)
+    port = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    try:
+        ref = cpu_reference_rate(seconds)
+    except Exception as e:  # a broken multiprocessing setup must not cost the GPU line
+        print("[bench] timing the Python reference failed: %r" % (e,), file=sys.stderr)
+        ref = None
+    return (ref or port), port
+
+
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's algorithm for this path on the host CPU.  The reference is
-    pure Python and cannot travel to the GPU box, so this times its C restatement (the oracle port)
-    on all host threads; the unmodified Python server measured in the build container is quoted in
-    DESIGN.md §6."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores — the unmodified
+    Python server + gym wrapper staged under oracle/_ref (one process per core), each step a bounded sample of the
+    same workload; the compiled C restatement (the oracle port) is reported next to it as `cpu_baseline_port`."""
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    budget = min(60.0, max(5.0, 0.05 * (steps + warm)))
-    rate, threads, sample, el = cpu_oracle_rate(budget, seed=args.seed)
+    budget = min(30.0, max(5.0, 0.03 * (steps + warm)))
+    t0 = time.perf_counter()
+    main_line, port = cpu_baselines(budget, args.seed)
+    rate = main_line["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i32/f64", "data": "synthetic", "config": workload_config(args, world),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": main_line, "cpu_baseline_port": port,
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "elapsed_s": el,
+        "gpu_launches": 0, "elapsed_s": time.perf_counter() - t0,
     }
     _emit(line)
 
@@ -126,53 +164,70 @@ def run_reference_arm(args, rank, world):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, polled through NVML from a thread for the whole run (started before
+    the warm-up); `report(t0, t1)` summarises the samples whose timestamps fall inside the timed region."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.path = tempfile.mktemp(prefix="evg_clocks_", suffix=".csv")
-        self.proc = None
+    def __init__(self, device):
+        self.samples = []  # (perf_counter, sm_mhz, reasons bitmask)
+        self.stop_flag = False
+        self.thread = None
+        self.h = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[device.index]) if vis and vis.split(",")[0].isdigit() else device.index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:
+            print("[bench] NVML unavailable: %r" % (e,), file=sys.stderr)
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = reasons_fn(self.h)
+                self.samples.append((time.perf_counter(), float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for ln in open(self.path):
-                p = [x.strip() for x in ln.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, p[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+
+    def report(self, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "NVML, polled every ~2 ms"}
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        if not inside and self.samples:
+            # a region shorter than one poll: the nearest samples on either side of it
+            before = [x for x in self.samples if x[0] < t0][-2:]
+            after = [x for x in self.samples if x[0] > t1][:2]
+            inside = before + after
+            out["source"] += "; region shorter than a poll, nearest samples used"
+        if inside:
+            mhz = sorted(x[1] for x in inside)
+            bits = 0
+            for x in inside:
+                bits |= x[2]
+            out.update(sm_mhz=mhz[len(mhz) // 2], samples=len(inside), reasons=sorted(k for k, v in self.BAD.items() if bits & v))
         return out
 
 
@@ -184,15 +239,18 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(envs_per_gpu):
-    """DRAM bytes per step-kernel launch from the committed ncu --set full capture, if one exists for
-    this batch size (profiles/step_kernel_traffic.json), else None."""
+def ncu_traffic(envs_per_gpu, phase):
+    """DRAM bytes per step-kernel launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture)
+    for THIS batch size and phase mix from profiles/step_kernel_traffic.json, else None: traffic measured on another
+    batch size or another part of the game is not this run's traffic."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
-        per_env = float(d["dram_bytes_per_env_turn"])
-        return per_env * envs_per_gpu
+        for c in d.get("captures", []):
+            if int(c["envs"]) == int(envs_per_gpu) and c.get("phase") == phase:
+                return float(c["dram_bytes_per_launch"])
     except Exception:
-        return None
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,10 +298,13 @@ def main():
     torch.cuda.set_device(dev)
     E = args.envs_per_gpu
     first, _ = rank * E, E
+    clocks = ClockSampler(dev)
+    clocks.start()  # before the warm-up: a poll thread needs no start-up time inside the timed region
     env = evgsim.BatchedEvergladesEnv(E, device=dev, seed=args.seed, auto_reset=evgsim._capi.AUTORESET_TERMINAL,
                                       env_id_offset=first)
     env.reset()
     stream = torch.cuda.current_stream(dev)
+    TL = env.num_turns
 
     fused = args.agents == "fused"
 
@@ -253,6 +314,14 @@ def main():
         else:
             env.step(env.random_actions())      # agent kernel, then the turn-step kernel
 
+    # ---- settle into the steady state (untimed, not part of --warmup): after turn t the matches with i mod TL == t
+    # start over, so match i ends up (TL - 1 - i mod TL) turns into its game and every phase is equally represented
+    if args.phase == "staggered":
+        phase_of = torch.arange(E, device=dev, dtype=torch.int32) % TL
+        for t in range(TL):
+            one_step()
+            env.reset(mask=(phase_of == t))
+        del phase_of
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize(dev)
@@ -261,12 +330,12 @@ def main():
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    stats0 = env.episode_stats()
     launches0 = env.launch_count
-    clocks.start()
+    wall0 = time.perf_counter()
     t_begin.record(stream)
     for k in range(K):
         a = None if fused else env.random_actions()
@@ -278,68 +347,113 @@ def main():
         ev[k][1].record(stream)
     t_end.record(stream)
     torch.cuda.synchronize(dev)
+    wall1 = time.perf_counter()
     if world > 1:
         dist.barrier()
-    clk = clocks.stop()
+    clk = clocks.report(wall0, wall1)
     launches = env.launch_count - launches0
-    step_kernel_name = {0: "evg_step_kernel (warp per match)", 1: "evg_step_tpm_kernel (thread per match)",
-                        2: "evg_step_pair_kernel (lane pair per match)"}.get(env._lib.evg_step_kernel_kind(env._h), "?")
+    stats1 = env.episode_stats()
+    fought = stats1["fought_unit_slots"] - stats0["fought_unit_slots"]  # unit slots that fought in the K timed turns
+    step_kernel_name = {0: "evg_step_kernel (warp per match)",
+                        1: "evg_step_tpm_kernel (thread per match)"}.get(env._lib.evg_step_kernel_kind(env._h), "?")
     total_ms = t_begin.elapsed_time(t_end)
     step_kernel_ms = sum(a.elapsed_time(b) for a, b in ev) / K
 
     # ---- end-to-end through the public host-buffer API (pinned host memory, copies inside)
     Ke = max(1, min(args.e2e_steps, K))
-    hb = env.host_buffers()
     ring = []
     for _ in range(4):  # pre-drawn host-side action rows (random_actions ignores observations)
         ring.append(env.random_actions().cpu().pin_memory())
         env.step(env._actions)
-    for _ in range(3):
-        env.step_host(ring[0])
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sink = 0.0
-    e0.record(stream)
-    for k in range(Ke):
-        obs_h, rew_h, done_h, _ = env.step_host(ring[k % 4], sync=True)
-        sink += float(rew_h[0, 0])  # the host reads the step's result
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    e2e_ms = e0.elapsed_time(e1)
+
+    def time_e2e(fmt):
+        from evgsim import hostmem
+        env.host_buffers(fmt)
+        placement = hostmem.last_placement()
+        for _ in range(3):
+            env.step_host(ring[0], obs_format=fmt)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sink = 0.0
+        e0.record(stream)
+        for k in range(Ke):
+            obs_h, rew_h, done_h, _ = env.step_host(ring[k % 4], sync=True, obs_format=fmt)
+            sink += float(obs_h[0, 0].sum()) + float(rew_h[0, 0])  # the host reads the step's result
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), placement
+
+    def d2h_probe(nbytes):
+        """Plain pinned D2H copy of as many bytes as the headline e2e format moves per step: the link's own speed."""
+        from evgsim import hostmem
+        src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dst = hostmem.pinned_empty((nbytes,), torch.uint8, dev.index)
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / 5
+
+    e2e_ms, placement = time_e2e(args.e2e_format)
+    e2e_f32_ms, _ = time_e2e("f32") if args.e2e_format != "f32" else (e2e_ms, None)
+    probe_ms = d2h_probe(env.d2h_bytes_per_step(args.e2e_format))
+    clocks.stop()
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, step_kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, step_kernel_ms, e2e_ms, e2e_f32_ms, probe_ms], dtype=torch.float64, device=dev)
+    f = torch.tensor([fought], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, step_kernel_ms, e2e_ms = (float(x) for x in t.tolist())
-    stats = evd.gather_episode_stats(env.episode_stats(), device=dev)  # the only collective; not timed
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    total_ms, step_kernel_ms, e2e_ms, e2e_f32_ms, probe_ms = (float(x) for x in t.tolist())
+    fought_all = int(f.item())
+    stats = evd.gather_episode_stats(stats1, device=dev)  # the only collective; not timed
 
     if rank == 0:
         total_envs = E * world
         value = total_envs * K / (total_ms / 1e3)
         e2e_value = total_envs * Ke / (e2e_ms / 1e3)
         peak, peak_src = measured_hbm_peak()
-        achieved = E * B_ALG / (step_kernel_ms / 1e3) / 1e9  # GB/s per GPU, step kernel alone
+        slots_per_env_turn = fought_all / float(total_envs * K)
+        b_alg = B_ALG_FIXED + B_ALG_PER_FOUGHT_SLOT * slots_per_env_turn
+        achieved = E * b_alg / (step_kernel_ms / 1e3) / 1e9  # GB/s per GPU, step kernel alone
+        d2h = env.d2h_bytes_per_step(args.e2e_format)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i32/f64", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step() * world,
-                    "d2h_bytes_per_step": env.d2h_bytes_per_step() * world, "steps": Ke, "ms_per_step": e2e_ms / Ke,
-                    "api": "BatchedEvergladesEnv.step_host (evg_step_host), pinned host buffers"},
+                    "d2h_bytes_per_step": d2h * world, "steps": Ke, "ms_per_step": e2e_ms / Ke,
+                    "obs_format": args.e2e_format,
+                    "api": "BatchedEvergladesEnv.step_host(obs_format=%r) (evg_step_host_fmt), pinned host buffers; the host gets "
+                           "every match's observations (lossless; evgsim.wire.expand == the float32 vector), rewards and done flags" % args.e2e_format,
+                    "pinned_placement": placement,
+                    "link": {"d2h_probe_ms": probe_ms, "d2h_probe_gbs_per_gpu": d2h / (probe_ms / 1e3) / 1e9,
+                             "e2e_d2h_gbs_per_gpu": d2h / (e2e_ms / Ke / 1e3) / 1e9,
+                             "note": "a plain pinned D2H copy of the same bytes per step on every rank at once: what the host link "
+                                     "allows; e2e_d2h_gbs_per_gpu / d2h_probe_gbs_per_gpu is how close the step gets to it"}},
+            "e2e_f32": {"value": total_envs * Ke / (e2e_f32_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_f32_ms / Ke,
+                        "d2h_bytes_per_step": env.d2h_bytes_per_step("f32") * world, "obs_format": "f32"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": step_kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(E), "peak_source": peak_src,
-                         "bytes_per_env_turn": B_ALG, "kernel_ms": step_kernel_ms,
-                         "kernel_env_turns_per_s": E / (step_kernel_ms / 1e3)},
+                         "frac": achieved / peak, "traffic": ncu_traffic(E, args.phase), "peak_source": peak_src,
+                         "bytes_per_env_turn": b_alg, "fought_unit_slots_per_env_turn": slots_per_env_turn,
+                         "bytes_formula": "1331 + 16 * fought unit slots per env-turn, slots counted on the device over the timed turns",
+                         "kernel_ms": step_kernel_ms, "kernel_env_turns_per_s": E / (step_kernel_ms / 1e3)},
             "episode_stats": stats,
         }
         if not args.no_cpu_baseline and world == 1:
-            rate, threads, sample, _ = cpu_oracle_rate(args.cpu_seconds, seed=args.seed)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+            line["cpu_baseline"], line["cpu_baseline_port"] = cpu_baselines(args.cpu_seconds, args.seed)
         _emit(line)
     if world > 1:
         dist.barrier()

@@ -22,6 +22,8 @@ AUTORESET_OFF, AUTORESET_TERMINAL, AUTORESET_NEXT = 0, 1, 2
 STATUS_IN_PROGRESS, STATUS_TIME_EXPIRED, STATUS_BASE_CAPTURE, STATUS_ANNIHILATION = 0, 1, 2, 3
 SHAPE_NORMALIZED_SCORE, SHAPE_BASIC, SHAPE_PENALIZE_LONG, SHAPE_SHORT_GAMES = 0, 1, 2, 3
 AGENT_EXTERNAL, AGENT_RANDOM, AGENT_BASE_RUSH, AGENT_SWARM = 0, 1, 2, 3
+OBS_F32, OBS_I16, OBS_WIRE = 0, 1, 2
+WIRE_NODE0 = 4
 BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_AGENTS, BIND_COUNT = 0, 1, 2, 3, 4, 5
 
 _N1 = MAX_NODES + 1
@@ -105,6 +107,7 @@ class EvgEpisodeStats(C.Structure):
         ("total_score", C.c_int64 * 2),
         ("status_count", C.c_int64 * 4),
         ("env_turns", C.c_int64),
+        ("fought_unit_slots", C.c_int64),
     ]
 
 
@@ -150,6 +153,10 @@ SYMBOLS = [
     ("evg_step", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_step_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_step_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("evg_obs_row_bytes", C.c_int, [_P, C.c_int32]),
+    ("evg_reset_fmt", C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    ("evg_step_fmt", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("evg_step_host_fmt", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_export_state", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     ("evg_import_state", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     ("evg_episode_stats", C.c_int, [_P, C.POINTER(EvgEpisodeStats), _P]),

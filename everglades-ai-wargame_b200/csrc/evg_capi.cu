@@ -40,10 +40,6 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-#ifndef EVG_DEFAULT_PAIR
-#define EVG_DEFAULT_PAIR false
-#endif
-
 struct EvgSim {
     EvgConfig cfg;
     evg::Tables tables;
@@ -56,8 +52,7 @@ struct EvgSim {
     int64_t launches;
     int64_t steps;
     EvgLayout layout;
-    bool use_tpm;     // a row-based step kernel (tpm / pair) or the warp-per-match one (EVG_STEP_KERNEL=warp)
-    bool use_pair;    // two lanes per match (EVG_STEP_KERNEL=pair) instead of one thread per match (=tpm)
+    bool use_tpm;     // the thread-per-match step kernel, or the warp-per-match one (small batches, EVG_STEP_KERNEL=warp)
     const uint4* tables_dev;  // Tables in device memory (inside bind slot EVG_BIND_TABLES)
     // evg_step_host's chunk pipeline: two streams of the library's own, created on first use
     cudaStream_t host_stream[2] = {nullptr, nullptr};
@@ -65,8 +60,6 @@ struct EvgSim {
     size_t tpm_smem;
     int tpm_grid;     // persistent CTAs: SMs x resident CTAs
     int tpm_threads;  // 128, or 32 (one warp per CTA) for small batches
-    size_t pair_smem;
-    int pair_grid;
 };
 
 namespace {
@@ -203,14 +196,6 @@ int build_tables(const EvgConfig& c, uint64_t seed, int64_t env_id_offset, evg::
     // u8 damage histograms when no target can collect > 255 damage in a turn
     t.tpm_hist16 = max_dmg_sum > 255 ? 1 : 0;
     t.max_damage_sum = max_dmg_sum;
-    {   // lane-pair kernel: per-thread row = padded record + scratch with per-match histograms
-        t.pair_hwords = (max_units * (t.tpm_hist16 ? 2 : 1) + 3) / 4;
-        const int scr_combat = 2 * nn + 2 * t.pair_hwords, scr_post = 2 * nn + 32;
-        int pitch = t.rec_words8 * 2 + (scr_combat > scr_post ? scr_combat : scr_post);
-        pitch += pitch & 1;
-        if (((pitch / 2) & 1) == 0) pitch += 2;  // pitch/2 odd: conflict-free 4- and 8-byte column accesses
-        t.pair_pitch = pitch;
-    }
     {   // thread-per-match kernel: per-thread row = the record's used words + the observation staging window; two
         // words per node and match are kept word-major per warp; the damage histograms of one round (<= 32
         // fighting groups) live in a per-warp pool
@@ -342,10 +327,6 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     // default: a thread per match, except for small batches, where a warp per match spreads the few matches over all
     // SMs (measured: 4,096 matches 2.0e8 vs 1.2e8 env-turns/s; break-even near 16k, profiles/README.md)
     s->use_tpm = which ? strcmp(which, "warp") != 0 : n_envs >= 12288;
-    s->use_pair = which ? strcmp(which, "pair") == 0 : EVG_DEFAULT_PAIR;
-    int pair_per_sm = 0;
-    if ((e = evg::pair_prepare(t, &s->pair_smem, &pair_per_sm)) != cudaSuccess || pair_per_sm < 1) { delete s; return cuda_fail(e, "lane-pair kernel setup"); }
-    s->pair_grid = prop.multiProcessorCount * pair_per_sm;
     // mid-size batches: one warp per CTA spreads the warps over all SMs (measured: +9 % at 65,536 matches, +5 % at
     // 32,768, slower from 98,304 on where the 128-thread CTAs' shared instruction stream wins; profiles/README.md)
     {
@@ -446,10 +427,38 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
     return EVG_OK;
 }
 
-int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream)
+int evg_obs_row_bytes(const EvgSim* sim, int32_t format)
+{
+    if (!sim) return 0;
+    switch (format) {
+        case EVG_OBS_F32: return 2 * sim->layout.obs_len * 4;
+        case EVG_OBS_I16: return 2 * sim->layout.obs_len * 2;
+        case EVG_OBS_WIRE: return evg::wire_bytes(sim->cfg.n_nodes);
+        default: return 0;
+    }
+}
+
+namespace {
+
+// format checks shared by the *_fmt entry points; `rows`/`f32` may be NULL where the caller allows it
+int check_fmt(const EvgSim* sim, int32_t format, const void* rows, const float* f32, const char* who)
+{
+    if (format < EVG_OBS_F32 || format > EVG_OBS_WIRE) return fail(EVG_E_ARG, "%s: unknown observation format %d", who, format);
+    if (format == EVG_OBS_I16) {
+        if (rows && !f32) return fail(EVG_E_ARG, "%s: EVG_OBS_I16 needs the float32 scratch d_obs_f32", who);
+        if (sim->cfg.turn_limit > 32767) return fail(EVG_E_ARG, "%s: EVG_OBS_I16 cannot carry a turn counter up to %d", who, sim->cfg.turn_limit);
+    }
+    if (rows && (uintptr_t)rows % 16) return fail(EVG_E_ARG, "%s: observation rows must be 16-byte aligned", who);
+    return EVG_OK;
+}
+
+}  // namespace
+
+int evg_reset_fmt(EvgSim* sim, int32_t format, const uint8_t* d_mask, void* d_rows, float* d_obs_f32, void* stream)
 {
     int rc = check_sim(sim, true);
     if (rc) return rc;
+    if ((rc = check_fmt(sim, format, d_rows, d_obs_f32, "evg_reset_fmt"))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (!d_mask) {
@@ -457,18 +466,25 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream)
         if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_AGENTS], 0, (size_t)sim->n_envs * 16, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agent state)");
         sim->steps = 0;
     }
-    e = evg::launch_reset(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], d_mask, d_obs,
-                          sim->n_envs, sim->grid, sim->smem, st);
+    const bool i16 = format == EVG_OBS_I16 && d_rows;
+    e = evg::launch_reset(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], d_mask,
+                          i16 ? (void*)d_obs_f32 : d_rows, format == EVG_OBS_WIRE ? EVG_OBS_WIRE : EVG_OBS_F32, sim->n_envs, sim->grid, sim->smem, st);
     if (e != cudaSuccess) return cuda_fail(e, "evg_reset_kernel launch");
     sim->launches += 1;
+    if (i16) {  // (with a mask the unmasked matches' rows are rewritten from the scratch as well: it holds their last observation)
+        if ((e = evg::launch_obs_to_i16(d_obs_f32, (int16_t*)d_rows, sim->n_envs * 2 * sim->layout.obs_len, st)) != cudaSuccess) return cuda_fail(e, "evg_obs_to_i16_kernel launch");
+        sim->launches += 1;
+    }
     return EVG_OK;
 }
 
+int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) { return evg_reset_fmt(sim, EVG_OBS_F32, d_mask, d_obs, nullptr, stream); }
+
 // first/count: the whole batch (0, n_envs), or a 128-aligned sub-range for the thread-per-match kernel (evg_step_host's
 // chunks; all the per-match arrays are offset here, the kernel adds `first` to the global match ids)
-static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_actions, int8_t* d_actions_out, float* d_obs,
+static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_actions, int8_t* d_actions_out, void* d_obs,
                      float* d_reward, uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream, int64_t first = 0,
-                     int64_t count = -1)
+                     int64_t count = -1, int obs_fmt = EVG_OBS_F32)
 {
     evg::StepArgs a;
     a.agent[0] = agent0;
@@ -478,7 +494,8 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.health = (double*)sim->bound[EVG_BIND_HEALTH];
     a.stats = (unsigned long long*)sim->bound[EVG_BIND_STATS];
     a.actions = d_actions;
-    a.obs = d_obs;
+    a.obs = (float*)d_obs;
+    a.obs_fmt = obs_fmt;
     a.reward = d_reward;
     a.done = d_done;
     a.status = d_status;
@@ -492,7 +509,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
         a.health += first * t.health_slots;
         if (a.actions) a.actions += first * 2 * EVG_MAX_ACTIONS * 2;
         if (a.actions_out) a.actions_out += first * 2 * EVG_MAX_ACTIONS * 2;
-        a.obs += first * 2 * t.obs_len;
+        a.obs = (float*)((char*)d_obs + first * (obs_fmt == EVG_OBS_WIRE ? evg::wire_bytes(t.n_nodes) : 2 * t.obs_len * 4));
         a.reward += first * 2;
         a.done += first;
         if (a.status) a.status += first;
@@ -500,9 +517,8 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
         a.n_envs = count;
         a.env_first = first;
     }
-    cudaError_t e = !sim->use_tpm  ? evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream)
-                    : sim->use_pair ? evg::launch_step_pair(sim->tables, a, sim->pair_smem, sim->pair_grid, (cudaStream_t)stream)
-                                    : evg::launch_step_tpm(sim->tables, a, sim->tpm_threads, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
+    cudaError_t e = !sim->use_tpm ? evg::launch_step(sim->tables, a, sim->grid, sim->smem, (cudaStream_t)stream)
+                                  : evg::launch_step_tpm(sim->tables, a, sim->tpm_threads, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;
     if (count < 0 || first == 0) sim->steps += 1;
@@ -544,58 +560,109 @@ int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_a
     return step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
 }
 
-int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done, int8_t* d_actions,
-                  float* d_obs, float* d_reward, uint8_t* d_done, void* stream)
+int evg_step_fmt(EvgSim* sim, int32_t format, const int8_t* d_actions, void* d_rows, float* d_obs_f32, float* d_reward,
+                 uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream)
 {
     int rc = check_sim(sim, true);
     if (rc) return rc;
-    if (!h_actions || !h_obs || !h_reward || !h_done) return fail(EVG_E_ARG, "evg_step_host: host buffers must be non-null");
+    if (!d_actions || !d_rows || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step_fmt: actions/rows/reward/done must be non-null");
+    if ((rc = check_fmt(sim, format, d_rows, d_obs_f32, "evg_step_fmt"))) return rc;
+    if (format != EVG_OBS_I16)
+        return step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_rows, d_reward, d_done, d_status, d_scores, stream, 0, -1, format);
+    if ((rc = step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs_f32, d_reward, d_done, d_status, d_scores, stream))) return rc;
+    cudaError_t e = evg::launch_obs_to_i16(d_obs_f32, (int16_t*)d_rows, sim->n_envs * 2 * sim->layout.obs_len, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_obs_to_i16_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
+int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void* h_rows, float* h_reward, uint8_t* h_done,
+                      int8_t* d_actions, void* d_rows, float* d_obs_f32, float* d_reward, uint8_t* d_done, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    const bool wire = format == EVG_OBS_WIRE, i16 = format == EVG_OBS_I16;
+    if (!h_actions || !h_rows || !d_actions || !d_rows || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_step_host: buffers must be non-null");
+    if (!wire && (!h_reward || !h_done)) return fail(EVG_E_ARG, "evg_step_host: h_reward/h_done may only be NULL with EVG_OBS_WIRE");
+    if ((rc = check_fmt(sim, format, d_rows, d_obs_f32, "evg_step_host_fmt"))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = sim->n_envs;
-    cudaError_t e;
+    const size_t ab = (size_t)sim->layout.action_bytes, rb = (size_t)evg_obs_row_bytes(sim, format), fb = (size_t)2 * sim->layout.obs_len * 4;
+    cudaError_t e = cudaSuccess;
+    const char* what = "";
+#define EVG_TRY(call, name) do { if (e == cudaSuccess && (e = (call)) != cudaSuccess) what = name; } while (0)
+    // one sub-range [first, first + cnt): H2D of its action rows, the step, (the narrowing,) D2H of its results, all on `cs`
+    auto chunk = [&](cudaStream_t cs, int64_t first, int64_t cnt, bool sub) -> int {
+        EVG_TRY(cudaMemcpyAsync(d_actions + first * ab, h_actions + first * ab, (size_t)cnt * ab, cudaMemcpyHostToDevice, cs), "H2D actions");
+        if (e != cudaSuccess) return EVG_OK;
+        int r = step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, i16 ? (void*)d_obs_f32 : d_rows, d_reward, d_done, nullptr,
+                          nullptr, cs, sub ? first : 0, sub ? cnt : -1, wire ? EVG_OBS_WIRE : EVG_OBS_F32);
+        if (r) return r;
+        if (i16) {
+            EVG_TRY(evg::launch_obs_to_i16((const float*)((const char*)d_obs_f32 + first * fb), (int16_t*)((char*)d_rows + first * rb),
+                                           cnt * 2 * sim->layout.obs_len, cs), "evg_obs_to_i16_kernel launch");
+            if (e == cudaSuccess) sim->launches += 1;
+        }
+        EVG_TRY(cudaMemcpyAsync((char*)h_rows + first * rb, (const char*)d_rows + first * rb, (size_t)cnt * rb, cudaMemcpyDeviceToHost, cs), "D2H observations");
+        if (h_reward) EVG_TRY(cudaMemcpyAsync(h_reward + first * 2, d_reward + first * 2, (size_t)cnt * 2 * 4, cudaMemcpyDeviceToHost, cs), "D2H reward");
+        if (h_done) EVG_TRY(cudaMemcpyAsync(h_done + first, d_done + first, (size_t)cnt, cudaMemcpyDeviceToHost, cs), "D2H done");
+        return EVG_OK;
+    };
     // Large batches on the thread-per-match kernel go through in chunks on two streams of the library's own, so that
-    // the D2H of one chunk (the PCIe-bound part: 840 B of observations per match) overlaps the H2D and the kernel of
-    // the next; everything is ordered after what `stream` holds now and `stream` waits for all of it.
+    // the D2H of one chunk (the PCIe-bound part) overlaps the H2D and the kernel of the next; everything is ordered
+    // after what `stream` holds now, and `stream` waits for all of it — on the error paths too: whatever was
+    // enqueued before a failure is joined into `stream` before the error is returned.
     int chunks = 8;
     if (const char* c = getenv("EVG_HOST_CHUNKS")) chunks = atoi(c);
-    if (chunks > 1 && sim->use_tpm && !sim->use_pair && n >= 65536) {
+    if (chunks > 1 && sim->use_tpm && n >= 65536) {
         if (!sim->host_start) {
-            if ((e = cudaEventCreateWithFlags(&sim->host_start, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+            cudaEvent_t ev0 = nullptr, ev[2] = {nullptr, nullptr};
+            cudaStream_t hs[2] = {nullptr, nullptr};
+            EVG_TRY(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming), "cudaEventCreate");
             for (int i = 0; i < 2; ++i) {
-                if ((e = cudaStreamCreateWithFlags(&sim->host_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-                if ((e = cudaEventCreateWithFlags(&sim->host_done[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+                EVG_TRY(cudaStreamCreateWithFlags(&hs[i], cudaStreamNonBlocking), "cudaStreamCreate");
+                EVG_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming), "cudaEventCreate");
             }
+            if (e != cudaSuccess) {  // nothing enqueued yet: release what was created and report
+                for (int i = 0; i < 2; ++i) {
+                    if (hs[i]) cudaStreamDestroy(hs[i]);
+                    if (ev[i]) cudaEventDestroy(ev[i]);
+                }
+                if (ev0) cudaEventDestroy(ev0);
+                return cuda_fail(e, what);
+            }
+            sim->host_start = ev0;
+            for (int i = 0; i < 2; ++i) { sim->host_stream[i] = hs[i]; sim->host_done[i] = ev[i]; }
         }
         const int64_t per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
-        const size_t ab = (size_t)sim->layout.action_bytes, ob = (size_t)2 * sim->layout.obs_len * 4;
-        if ((e = cudaEventRecord(sim->host_start, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-        for (int i = 0; i < 2; ++i)
-            if ((e = cudaStreamWaitEvent(sim->host_stream[i], sim->host_start, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+        EVG_TRY(cudaEventRecord(sim->host_start, st), "cudaEventRecord");
+        for (int i = 0; i < 2; ++i) EVG_TRY(cudaStreamWaitEvent(sim->host_stream[i], sim->host_start, 0), "cudaStreamWaitEvent");
         int c = 0;
-        for (int64_t first = 0; first < n; first += per, ++c) {
-            const int64_t cnt = n - first < per ? n - first : per;
-            cudaStream_t cs = sim->host_stream[c & 1];
-            if ((e = cudaMemcpyAsync(d_actions + first * ab, h_actions + first * ab, (size_t)cnt * ab, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return cuda_fail(e, "H2D actions");
-            rc = step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, nullptr, nullptr, cs, first, cnt);
-            if (rc) return rc;
-            if ((e = cudaMemcpyAsync((char*)h_obs + first * ob, (const char*)d_obs + first * ob, (size_t)cnt * ob, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return cuda_fail(e, "D2H obs");
-            if ((e = cudaMemcpyAsync(h_reward + first * 2, d_reward + first * 2, (size_t)cnt * 2 * 4, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return cuda_fail(e, "D2H reward");
-            if ((e = cudaMemcpyAsync(h_done + first, d_done + first, (size_t)cnt, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return cuda_fail(e, "D2H done");
-        }
+        for (int64_t first = 0; first < n && e == cudaSuccess && rc == EVG_OK; first += per, ++c)
+            rc = chunk(sim->host_stream[c & 1], first, n - first < per ? n - first : per, true);
+        // join: `stream` waits for both library streams whatever happened above
         for (int i = 0; i < 2; ++i) {
-            if ((e = cudaEventRecord(sim->host_done[i], sim->host_stream[i])) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-            if ((e = cudaStreamWaitEvent(st, sim->host_done[i], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+            cudaError_t j = cudaEventRecord(sim->host_done[i], sim->host_stream[i]);
+            if (j == cudaSuccess) j = cudaStreamWaitEvent(st, sim->host_done[i], 0);
+            if (j != cudaSuccess) {  // cannot even order the streams: drain them here so nothing outlives the call unordered
+                cudaStreamSynchronize(sim->host_stream[i]);
+                if (e == cudaSuccess) { e = j; what = "joining the chunk streams"; }
+            }
         }
-        return EVG_OK;
+    } else {
+        rc = chunk(st, 0, n, false);
     }
-    e = cudaMemcpyAsync(d_actions, h_actions, (size_t)n * sim->layout.action_bytes, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return cuda_fail(e, "H2D actions");
-    rc = evg_step(sim, d_actions, d_obs, d_reward, d_done, nullptr, nullptr, stream);
+#undef EVG_TRY
     if (rc) return rc;
-    if ((e = cudaMemcpyAsync(h_obs, d_obs, (size_t)n * 2 * sim->layout.obs_len * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H obs");
-    if ((e = cudaMemcpyAsync(h_reward, d_reward, (size_t)n * 2 * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H reward");
-    if ((e = cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H done");
+    if (e != cudaSuccess) return cuda_fail(e, what);
     return EVG_OK;
+}
+
+int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done, int8_t* d_actions,
+                  float* d_obs, float* d_reward, uint8_t* d_done, void* stream)
+{
+    if (!h_reward || !h_done) return fail(EVG_E_ARG, "evg_step_host: host buffers must be non-null");
+    return evg_step_host_fmt(sim, EVG_OBS_F32, h_actions, h_obs, h_reward, h_done, d_actions, d_obs, nullptr, d_reward, d_done, stream);
 }
 
 int evg_export_state(EvgSim* sim, int64_t first, int64_t count, EvgEnvState* d_states, void* stream)
@@ -641,6 +708,7 @@ int evg_episode_stats(EvgSim* sim, EvgEpisodeStats* host_out, void* stream)
     host_out->total_score[1] = (int64_t)h[evg::ST_SCORE1];
     for (int k = 0; k < 4; ++k) host_out->status_count[k] = (int64_t)h[evg::ST_STATUS0 + k];
     host_out->env_turns = sim->steps * sim->n_envs;
+    host_out->fought_unit_slots = (int64_t)h[evg::ST_FOUGHT];
     return EVG_OK;
 }
 
@@ -713,7 +781,7 @@ int evg_shape_reward(EvgSim* sim, int32_t mode, const float* d_reward, const uin
     return EVG_OK;
 }
 
-int evg_step_kernel_kind(const EvgSim* sim) { return !sim ? -1 : !sim->use_tpm ? 0 : sim->use_pair ? 2 : 1; }
+int evg_step_kernel_kind(const EvgSim* sim) { return !sim ? -1 : sim->use_tpm ? 1 : 0; }
 
 int64_t evg_launch_count(const EvgSim* sim) { return sim ? sim->launches : -1; }
 

@@ -40,7 +40,8 @@ struct alignas(16) Tables {
     int32_t n_nodes, obs_len, rec_words8, health_slots;
     int32_t turn_limit, capture_bonus, auto_reset, max_group_size;
     int32_t has_small_groups, hist_words, n_big, pad1;  // hist_words: u32 words per side of the damage histogram
-    uint32_t seed_lo, seed_hi, env_base, pad2;
+    uint32_t seed_lo, seed_hi, env_base;
+    uint32_t cta_fought;  // 0 here; in a CTA's shared-memory copy: unit slots its matches fought this launch (ST_FOUGHT)
     float max_score_f;
     float pad5;
     // per-warp shared-memory carve-up (bytes)
@@ -74,8 +75,7 @@ struct alignas(16) Tables {
     uint32_t node_cap[kNN];  // control points [0:16) | (TeamStart + 1) [16:18)
     uint32_t pad_t;
     uint64_t p1_nib;  // p1_map as nibbles (node i at bits [4i, 4i+4)) for maps of <= 15 nodes: a register lookup
-    // lane-pair kernel (evg_step_pair.cu): row pitch and per-side histogram words of its per-match histograms
-    int32_t pair_pitch, pair_hwords;
+    int32_t pad_p[2];
     const double* loss_tab;  // [type][node][bonus][32]: (10.*d)/(armor + bonus*StructureDefense), d < 32
     const double* rcp_tab;   // [type][node][bonus]: 1 / (armor + bonus*StructureDefense), correctly rounded
     int32_t fast_div;        // 1: (10.*d)/divisor == the two-FMA correction of (10.*d)*rcp for every reachable d (checked on the host)
@@ -104,7 +104,9 @@ constexpr int kTpmSmallThreads = 32;  // the one-warp-per-CTA instantiation for 
 constexpr int kTpmStage = EVG_TPM_STAGE;  // observation staging window per match, 32-bit words (16 or 32)
 
 // device statistics accumulators (uint64 each); matches EvgEpisodeStats minus env_turns
-enum { ST_EPISODES = 0, ST_WIN0, ST_WIN1, ST_TIES, ST_TURNS, ST_SCORE0, ST_SCORE1, ST_STATUS0, ST_COUNT = ST_STATUS0 + 4 };
+// ST_FOUGHT: unit slots of the groups that took part in combat (every match-turn, finished or not): the health term of
+// the step's algorithmic bytes is 16 B per such slot, so bench.py can state it for the turns it timed
+enum { ST_EPISODES = 0, ST_WIN0, ST_WIN1, ST_TIES, ST_TURNS, ST_SCORE0, ST_SCORE1, ST_STATUS0, ST_FOUGHT = ST_STATUS0 + 4, ST_COUNT };
 
 struct StepArgs {
     uint32_t* records;
@@ -122,7 +124,11 @@ struct StepArgs {
     const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
     int64_t env_first;        // thread-per-match kernel: this launch covers matches [env_first, env_first + n_envs) of the
                               // simulator (all pointers above are already offset); 0 for a whole-batch launch
+    int32_t obs_fmt;          // EVG_OBS_F32: `obs` is float32[n][2][obs_len]; EVG_OBS_WIRE: packed rows of wire_bytes(n_nodes)
 };
+
+// bytes of one match's wire row (include/evgsim.h, EVG_OBS_WIRE)
+__host__ __device__ inline int wire_bytes(int n_nodes) { return (EVG_WIRE_NODE0 + 4 * n_nodes + 3 * kGroupLanes + 8 + 15) / 16 * 16; }
 
 // Kernels that need more than 48 KB of dynamic shared memory are opted in up to the DEVICE limit, not up to what one
 // simulator needs: the attribute is per function, and simulators of different configurations share the functions.
@@ -137,8 +143,9 @@ inline cudaError_t optin_smem_limit(size_t needed, int* limit)
 
 // launchers (evg_kernels.cu); all asynchronous on `stream`, return the launch error
 cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, float* obs,
+cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, void* obs, int obs_fmt,
                          int64_t n_envs, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_obs_to_i16(const float* obs, int16_t* out, int64_t n_values, cudaStream_t stream);
 cudaError_t launch_export(const Tables& t, const uint32_t* records, const double* health, int64_t first, int64_t count,
                           EvgEnvState* out, cudaStream_t stream);
 cudaError_t launch_import(const Tables& t, uint32_t* records, double* health, int64_t first, int64_t count,
@@ -157,9 +164,6 @@ cudaError_t set_step_smem(size_t smem);
 bool tpm_has_small(const Tables& t);
 cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blocks_per_sm);
 cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, size_t smem, int max_grid, cudaStream_t stream);
-// two lanes per match (evg_step_pair.cu)
-cudaError_t pair_prepare(const Tables& t, size_t* smem_out, int* blocks_per_sm);
-cudaError_t launch_step_pair(const Tables& t, const StepArgs& a, size_t smem, int max_grid, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // Philox4x32-10 (Salmon et al., SC'11); same function as oracle/tape.py, oracle/evg_oracle.c.

@@ -87,12 +87,38 @@ __device__ __forceinline__ void node_accumulate(const Tables& S, const WarpSmem&
 
 // board_state (server.py:382-455) + player_state (server.py:457-501) + concat (env.py:158-171)
 // for both players, staged in shared memory and streamed out as one contiguous row.
+// fmt == EVG_OBS_WIRE: the packed row of include/evgsim.h instead (out = that match's row; done/status/rewards go into it).
 template <int NODES>
 __device__ __forceinline__ void pack_obs(const Tables& S, const WarpSmem& W, int lane, bool is_grp, int side, int gid,
-                                         uint32_t w0, uint32_t w1, uint32_t nw, uint32_t turn, float* out)
+                                         uint32_t w0, uint32_t w1, uint32_t nw, uint32_t turn, float* out, int fmt = EVG_OBS_F32,
+                                         bool done = false, int status = 0, float r0 = 0.f, float r1 = 0.f)
 {
     const Dim<NODES> D(S);
     const int L = D.obs_len(), nn = D.nn();
+    if (fmt == EVG_OBS_WIRE) {
+        uint32_t* sw = reinterpret_cast<uint32_t*>(W.obs);
+        const int n_nodes = D.n_nodes(), ww = wire_bytes(n_nodes) / 4, gw = 1 + n_nodes + 3 * kGroupLanes / 4;
+        if (lane == 0) {
+            sw[0] = turn | (done ? 1u : 0u) << 16 | (uint32_t)status << 24;
+            sw[gw] = __float_as_uint(r0);
+            sw[gw + 1] = __float_as_uint(r1);
+            for (int i = gw + 2; i < ww; ++i) sw[i] = 0u;
+        }
+        if (lane < n_nodes)  // node lane + 1: controlState, listed units of player 0, of player 1
+            sw[1 + lane] = (nw & 0xFFFFu) | (W.acc[lane + 1] & 255u) << 16 | (W.acc[nn + lane + 1] & 255u) << 24;
+        if (is_grp) {
+            uint8_t* b = reinterpret_cast<uint8_t*>(sw) + EVG_WIRE_NODE0 + 4 * n_nodes + 3 * lane;
+            b[0] = (uint8_t)((w0 & W0_LOC_MASK) | ((w0 >> 21) & 1u) << 6);
+            b[1] = (uint8_t)((w0 >> W0_AVG_SHIFT) & 127u);
+            b[2] = (uint8_t)__popc(w1 & 0xFFFFu);
+        }
+        __syncwarp();
+        uint2* o2 = reinterpret_cast<uint2*>(out);
+        const uint2* s2 = reinterpret_cast<const uint2*>(sw);
+        for (int i = lane; i < ww / 2; i += 32) __stcs(o2 + i, s2[i]);
+        __syncwarp();
+        return;
+    }
     if (lane == 0) {
         W.obs[0] = (float)turn;
         W.obs[L] = (float)turn;
@@ -190,6 +216,10 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
         const bool fighting = present && (peers & opp_lanes) != 0;
         const uint32_t fmask = __ballot_sync(FULL, fighting);
         if (fmask) {
+            {   // unit slots whose health this turn's combat reads and may write (ST_FOUGHT)
+                const unsigned slots = __reduce_add_sync(FULL, fighting ? (unsigned)S.g_size[lane] : 0u);
+                if (lane == 0) atomicAdd(&cta_stats[ST_FOUGHT], (unsigned long long)slots);
+            }
             // Histogram slot of a target = (units of its side's fighting groups at lower-numbered nodes)
             // + (units of its side's groups listed before it at its node) + alive rank inside the group.
             // Inside one node that is exactly the uid the reference draws (uid -> (group,
@@ -421,14 +451,16 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
 
     // ---- reward / done, env.py:37-60.  float32(float64(score)/MAX_SCORE) == float32 IEEE division for
     // every score < 2^24 (no double-rounding case exists; checked exhaustively in tests/test_tape.py).
+    float rw0, rw1;
     {
         const int mine = lane ? s1 : s0, other = lane ? s0 : s1;
         float r;
         if (done) r = mine == other ? 0.f : (mine > other ? 1.f : (lane ? -1.f : 0.f));
         else r = __fdiv_rn((float)mine, S.max_score_f);
-        const float r1 = __shfl_sync(FULL, r, 1);
+        rw1 = __shfl_sync(FULL, r, 1);
+        rw0 = __shfl_sync(FULL, r, 0);
         if (lane == 0) {
-            reinterpret_cast<float2*>(A.reward)[env] = make_float2(r, r1);
+            reinterpret_cast<float2*>(A.reward)[env] = make_float2(rw0, rw1);
             A.done[env] = done ? 1 : 0;
             if (A.status) A.status[env] = (uint8_t)status;
             if (A.scores) reinterpret_cast<int2*>(A.scores)[env] = make_int2(s0, s1);
@@ -436,8 +468,10 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
     }
 
     // ---- observations of the post-turn state
-    float* obs_out = A.obs + env * 2 * D.obs_len();
-    pack_obs<NODES>(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, obs_out);
+    const int fmt = A.obs_fmt;
+    float* obs_out = fmt == EVG_OBS_WIRE ? reinterpret_cast<float*>(reinterpret_cast<char*>(A.obs) + env * wire_bytes(n_nodes))
+                                         : A.obs + env * 2 * D.obs_len();
+    pack_obs<NODES>(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, obs_out, fmt, done, status, rw0, rw1);
 
     // ---- termination with in-place auto-reset
     if (done && S.auto_reset != EVG_AUTORESET_OFF) {
@@ -457,7 +491,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
         for (int i = lane; i < S.health_slots; i += 32) hp[i] = 100.0;  // definitions.py:62
         if (S.auto_reset == EVG_AUTORESET_NEXT) {
             node_accumulate<NODES>(S, W, lane, is_grp, side, w0, w1);
-            pack_obs<NODES>(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, obs_out);
+            pack_obs<NODES>(S, W, lane, is_grp, side, gid, w0, w1, nw, turn, obs_out, fmt, done, status, rw0, rw1);
         }
     }
 
@@ -499,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 4) evg_step_kernel(const __grid_cons
 // capture() at turn 0 -> bases at +-controlPoints); writes the first observation.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) evg_reset_kernel(const __grid_constant__ Tables T, uint32_t* records, double* health,
-                                                             const uint8_t* mask, float* obs, int64_t n_envs)
+                                                             const uint8_t* mask, void* obs, int obs_fmt, int64_t n_envs)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables& S = stage_tables(T, smem);
@@ -526,7 +560,9 @@ __global__ void __launch_bounds__(kThreads) evg_reset_kernel(const __grid_consta
         for (int i = lane; i < S.health_slots; i += 32) hp[i] = 100.0;
         if (obs) {
             node_accumulate<0>(S, W, lane, is_grp, side, w0, w1);
-            pack_obs<0>(S, W, lane, is_grp, side, gid, w0, w1, nw, 0u, obs + env * 2 * S.obs_len);
+            float* out = obs_fmt == EVG_OBS_WIRE ? reinterpret_cast<float*>(static_cast<char*>(obs) + env * wire_bytes(S.n_nodes))
+                                                 : static_cast<float*>(obs) + env * 2 * S.obs_len;
+            pack_obs<0>(S, W, lane, is_grp, side, gid, w0, w1, nw, 0u, out, obs_fmt);
         }
     }
 }
@@ -859,10 +895,33 @@ cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t sme
     return cudaGetLastError();
 }
 
-cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, float* obs, int64_t n_envs,
-                         int grid, size_t smem, cudaStream_t stream)
+cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, void* obs, int obs_fmt,
+                         int64_t n_envs, int grid, size_t smem, cudaStream_t stream)
 {
-    evg_reset_kernel<<<grid, kThreads, smem, stream>>>(t, records, health, mask, obs, n_envs);
+    evg_reset_kernel<<<grid, kThreads, smem, stream>>>(t, records, health, mask, obs, obs_fmt, n_envs);
+    return cudaGetLastError();
+}
+
+// EVG_OBS_I16: the float32 observation vector narrowed to int16 (every entry is an integer that fits), 8 values per thread
+__global__ void evg_obs_to_i16_kernel(const float4* __restrict__ obs, uint4* __restrict__ out, const float* __restrict__ obs1,
+                                      int16_t* __restrict__ out1, int64_t n8, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n8) {
+        const float4 a = __ldcs(obs + 2 * i), b = __ldcs(obs + 2 * i + 1);
+        auto pk = [](float lo, float hi) { return ((uint32_t)(int)lo & 0xFFFFu) | (uint32_t)(int)hi << 16; };
+        __stcs(out + i, make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), pk(b.z, b.w)));
+    } else if (i == n8) {
+        for (int64_t k = 8 * n8; k < n; ++k) out1[k] = (int16_t)(int)obs1[k];  // the last 0..7 values
+    }
+}
+
+cudaError_t launch_obs_to_i16(const float* obs, int16_t* out, int64_t n_values, cudaStream_t stream)
+{
+    if (n_values <= 0) return cudaSuccess;
+    const int64_t n8 = n_values / 8;
+    evg_obs_to_i16_kernel<<<(unsigned)((n8 + 1 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(obs), reinterpret_cast<uint4*>(out),
+                                                                               obs, out, n8, n_values);
     return cudaGetLastError();
 }
 

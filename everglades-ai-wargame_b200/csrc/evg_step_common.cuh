@@ -1,5 +1,4 @@
-// evg_step_common.cuh — device helpers shared by the thread-per-match (evg_step_tpm.cu) and the
-// lane-pair-per-match (evg_step_pair.cu) step kernels.
+// evg_step_common.cuh — device helpers of the thread-per-match step kernel (evg_step_tpm.cu).
 #pragma once
 #include "evg_internal.h"
 

@@ -134,7 +134,9 @@ __device__ __noinline__ void load_rows_direct(const StepArgs& A, uint32_t* wrow,
 // leaves that code out, the kernel's instruction footprint being what its instruction cache misses are made of
 // THREADS: 128 (a CTA = 4 warps sharing tables, barrier and instruction stream), or 32 for small batches: one warp
 // per CTA spreads a few thousand matches over all SMs instead of a fifth of them.
-template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS, int THREADS>
+// WIRE: the observation output is the packed wire row of include/evgsim.h (EVG_OBS_WIRE: 128 bytes per match on DemoMap,
+// both players' observations + rewards + done in one cache line) instead of float32[2][obs_len] (840 bytes)
+template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS, int THREADS, bool WIRE = false>
 __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_CTAS : 1) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     uint32_t turn = 0, episode = 0;
     int s0 = 0, s1 = 0, status = 0;
     bool done = false;
+    float r0 = 0.f, r1 = 0.f;
     if (valid) {
         turn = R[kRecTurn] + 1u;  // server.py:214
         episode = R[kRecEpisode];
@@ -349,14 +352,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                     if (__popc(R[2 * L + 1] & 0xFFFFu) > 8) xm |= 1u << L;
                 }
             // the health rows of the groups that will fight: start them towards L2 now
-            {
+            if (fm) {
                 const char* he = reinterpret_cast<const char*>(A.health + env * S.health_slots);
+                uint32_t slots = 0;
                 for (uint32_t m = fm; m; m &= m - 1) {
                     const int L = __ffs(m) - 1;
                     const char* hr = he + (size_t)S.g_slot[L] * 8;
+                    const uint32_t size = S.g_size[L];
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(hr));
-                    if (S.g_size[L] > 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + 64));
+                    if (size > 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(hr + 64));
+                    slots += size;
                 }
+                // ST_FOUGHT: unit slots whose health this turn's combat reads; gathered per CTA in a spare table word
+                atomicAdd(&reinterpret_cast<Tables*>(smem)->cta_fought, slots);
             }
         }
         __syncwarp();  // rows (actions applied, node words) are read by other lanes from here on
@@ -578,7 +586,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         done = status != 0;
 
         // ---- reward / done, env.py:37-60 (float32 division == float32(float64 quotient), tests/test_tape.py)
-        float r0, r1;
         if (done) {
             r0 = s0 > s1 ? 1.f : 0.f;
             r1 = s1 > s0 ? 1.f : (s1 < s0 ? -1.f : 0.f);
@@ -607,67 +614,92 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     EVG_PHASE_SYNC(3);
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
-    // Each thread packs kTpmStage floats at a time into the staging window of its row; the warp streams the
-    // windows out as contiguous float2 runs (64 / kTpmStage matches x 4 * kTpmStage bytes per store instruction).
+    // Each thread packs kTpmStage words at a time into the staging window of its row; the warp streams the
+    // windows out as contiguous 8-byte runs (64 / kTpmStage matches x 4 * kTpmStage bytes per store instruction).
+    // The output row of a match is either float32[2][obs_len] (the reference's vector) or, WIRE, the packed row of
+    // include/evgsim.h (EVG_OBS_WIRE) that holds the same information once, with the step's rewards and done flag.
     {
-        constexpr int SP = kTpmStage / 2;   // float2 per window
+        constexpr int SP = kTpmStage / 2;   // 8-byte pairs per window
         constexpr int MPI = 32 / SP;        // matches per store instruction
-        float2* stage = reinterpret_cast<float2*>(R + RWU);  // P and RWU are even: 8-byte aligned
+        uint2* stage = reinterpret_cast<uint2*>(R + RWU);  // P and RWU are even: 8-byte aligned
         const int stage_off = RWU;
-        const int npairs = OL;  // 2*OL floats per match = OL float2
-        float* obs_base = A.obs + warp_env0 * 2 * OL;
-        auto value = [&](int f) -> float {  // f = index into the match's 2*OL floats
+        const int WW = (EVG_WIRE_NODE0 + 4 * n_nodes + 3 * kGroupLanes + 8 + 15) / 16 * 4;  // words of a wire row
+        const int npairs = WIRE ? WW / 2 : OL;  // 8-byte pairs per match (2*OL floats = OL pairs)
+        uint32_t* obs_base = reinterpret_cast<uint32_t*>(A.obs) + warp_env0 * 2 * npairs;
+        auto value = [&](int f) -> uint32_t {  // float32 format: the bits of entry f of the match's 2*OL floats
             const int p = f >= OL ? 1 : 0, i = f - p * OL;
-            if (i == 0) return (float)turn;
+            if (i == 0) return __float_as_uint((float)turn);
             if (i < 1 + 4 * n_nodes) {
                 const int k = (i - 1) >> 2, j = (i - 1) & 3;
                 const int x = p ? (int)p1map((uint32_t)(k + 1)) : k + 1;  // server.py:437-439
                 if (j < 2) {  // 'DEFENSE' / 'OBSERVE' in resource, :442-443: both flags of a node from one 8-byte load
                     const float2 c2 = ocpair[p * n_nodes + k];
-                    return j ? c2.y : c2.x;
+                    return __float_as_uint(j ? c2.y : c2.x);
                 }
-                if (j == 2) return (float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu);  // raw sign for both viewers
-                return (float)(X[32 * ((p ? 0 : nn) + x)] & 1023u);                                  // opposing listed units
+                if (j == 2) return __float_as_uint((float)(int)(int16_t)(R[kRecNode0 + x - 1] & 0xFFFFu));  // raw sign for both viewers
+                return __float_as_uint((float)(X[32 * ((p ? 0 : nn) + x)] & 1023u));                          // opposing listed units
             }
             const int q = i - 1 - 4 * n_nodes, g = q / 5, j = q - 5 * g;
             const int L = p * EVG_NUM_GROUPS + g;
             const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);  // one 8-byte load serves a group's five entries
             const uint32_t w0 = w.x;
-            if (j == 0) return (float)(p ? p1map(w0 & W0_LOC_MASK) : (w0 & W0_LOC_MASK));
-            if (j == 1) return oconst[f];  // unit type id
-            if (j == 2) return (float)((w0 >> W0_AVG_SHIFT) & 127u);
-            if (j == 3) return (float)((w0 >> 21) & 1u);
-            return (float)__popc(w.y & 0xFFFFu);
+            if (j == 0) return __float_as_uint((float)(p ? p1map(w0 & W0_LOC_MASK) : (w0 & W0_LOC_MASK)));
+            if (j == 1) return __float_as_uint(oconst[f]);  // unit type id
+            if (j == 2) return __float_as_uint((float)((w0 >> W0_AVG_SHIFT) & 127u));
+            if (j == 3) return __float_as_uint((float)((w0 >> 21) & 1u));
+            return __float_as_uint((float)__popc(w.y & 0xFFFFu));
+        };
+        // wire format: a group's three bytes = location (real numbering) | moving << 6, avg health, units alive
+        auto gwire = [&](int L) -> uint32_t {
+            const uint2 w = *reinterpret_cast<const uint2*>(R + 2 * L);
+            return (w.x & W0_LOC_MASK) | ((w.x >> 21) & 1u) << 6 | ((w.x >> W0_AVG_SHIFT) & 127u) << 8 | (uint32_t)__popc(w.y & 0xFFFFu) << 16;
+        };
+        auto wire = [&](int w) -> uint32_t {  // word w of the wire row
+            if (w == 0) return turn | (done ? 1u : 0u) << 16 | (uint32_t)status << 24;
+            if (w <= n_nodes)  // node w: controlState int16, listed units of player 0, of player 1 (:446-449)
+                return (R[kRecNode0 + w - 1] & 0xFFFFu) | (X[32 * w] & 255u) << 16 | (X[32 * (nn + w)] & 255u) << 24;
+            const int wi = w - 1 - n_nodes;
+            if (wi < 18) {  // 24 groups x 3 bytes = 6 quads of 3 words
+                const int q = wi / 3, r = wi - 3 * q;
+                const uint32_t a = gwire(4 * q + r), b = gwire(4 * q + r + 1);
+                return r == 0 ? (a | b << 24) : r == 1 ? (a >> 8 | b << 16) : (a >> 16 | b << 8);
+            }
+            if (wi == 18) return __float_as_uint(r0);
+            if (wi == 19) return __float_as_uint(r1);
+            return 0u;
         };
         const int sub = lane / SP, cp = lane % SP;
         const int nchunks = (npairs + SP - 1) / SP;
+        constexpr int kFastChunks = WIRE ? ((EVG_WIRE_NODE0 + 4 * NODES + 3 * kGroupLanes + 8 + 15) / 16 * 2 + SP - 1) / SP
+                                         : (1 + 4 * NODES + 60 + SP - 1) / SP;
 #pragma unroll
-        for (int c = 0; c < (NODES ? (1 + 4 * NODES + 60 + SP - 1) / SP : nchunks); ++c) {
+        for (int c = 0; c < (NODES ? kFastChunks : nchunks); ++c) {
             if (valid) {
-                float vals[2 * SP];  // all reads first (they can be merged and overlapped), then the staging stores
+                uint32_t vals[2 * SP];  // all reads first (they can be merged and overlapped), then the staging stores
 #pragma unroll
-                for (int k = 0; k < 2 * SP; ++k) vals[k] = 2 * SP * c + k < 2 * npairs ? value(2 * SP * c + k) : 0.f;
+                for (int k = 0; k < 2 * SP; ++k)
+                    vals[k] = 2 * SP * c + k < 2 * npairs ? (WIRE ? wire(2 * SP * c + k) : value(2 * SP * c + k)) : 0u;
 #pragma unroll
                 for (int k = 0; k < SP; ++k)
-                    if (SP * c + k < npairs) stage[k] = make_float2(vals[2 * k], vals[2 * k + 1]);
+                    if (SP * c + k < npairs) stage[k] = make_uint2(vals[2 * k], vals[2 * k + 1]);
             }
             __syncwarp();
             const int pr = SP * c + cp;
             if (pr < npairs) {
                 const uint32_t* srow = wrow + stage_off + 2 * cp;
-                float* orow = obs_base + 2 * pr;
+                uint32_t* orow = obs_base + 2 * pr;
                 if (nvalid == 32) {  // whole warp: no per-match predicates
 #pragma unroll
                     for (int it = 0; it < 32 / MPI; ++it) {
                         const int m = MPI * it + sub;
-                        const float2 v = *reinterpret_cast<const float2*>(srow + (size_t)m * P);
-                        __stcs(reinterpret_cast<float2*>(orow + (size_t)m * 2 * OL), v);
+                        const uint2 v = *reinterpret_cast<const uint2*>(srow + (size_t)m * P);
+                        __stcs(reinterpret_cast<uint2*>(orow + (size_t)m * 2 * npairs), v);
                     }
                 } else {
 #pragma unroll 1
                     for (int m = sub; m < nvalid; m += MPI) {
-                        const float2 v = *reinterpret_cast<const float2*>(srow + (size_t)m * P);
-                        __stcs(reinterpret_cast<float2*>(orow + (size_t)m * 2 * OL), v);
+                        const uint2 v = *reinterpret_cast<const uint2*>(srow + (size_t)m * P);
+                        __stcs(reinterpret_cast<uint2*>(orow + (size_t)m * 2 * npairs), v);
                     }
                 }
             }
@@ -713,6 +745,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     }
     __syncwarp();
     }  // batch loop
+    __syncthreads();
+    if (threadIdx.x == 0 && S.cta_fought) atomicAdd(&A.stats[ST_FOUGHT], (unsigned long long)S.cta_fought);
 }
 
 // DemoMap row: 62 record words + the staging window, pitch / 2 odd
@@ -731,28 +765,38 @@ Variant pick(const Tables& t)
 
 bool tpm_has_small(const Tables& t) { return pick(t) == V_FAST; }
 
-cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blocks_per_sm)
+static size_t tpm_smem_bytes(const Tables& t, int threads)
 {
     size_t smem = (size_t)t.sm_tables_bytes + (size_t)(((2 * t.obs_len + 3) & ~3) * 4 + ((2 * t.n_nodes * 8 + 15) & ~15)) +
                   (size_t)(threads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
+    return smem;
+}
+
+cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blocks_per_sm)
+{
+    const size_t smem = tpm_smem_bytes(t, threads);
     *smem_out = smem;
     cudaError_t e;
     int limit = 0;
     if ((e = optin_smem_limit(smem, &limit)) != cudaSuccess) return e;
-#define EVG_TPM_ATTR(K) \
-    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+#define EVG_TPM_ATTR(...) \
+    if ((e = cudaFuncSetAttribute(evg_step_tpm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
     if (threads == kTpmSmallThreads) {
         if (pick(t) != V_FAST) return cudaErrorInvalidValue;
-        EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads>))
-        EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads>))
+        EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads)
+        EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads)
+        EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads, true)
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads>,
                                                              threads, smem);
     }
-    EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmThreads>))
-    EVG_TPM_ATTR((evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmThreads>))
-    EVG_TPM_ATTR((evg_step_tpm_kernel<0, 16, uint8_t, 0, true, kTpmThreads>))
-    EVG_TPM_ATTR((evg_step_tpm_kernel<0, 16, uint16_t, 0, true, kTpmThreads>))
+    EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmThreads)
+    EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, true, kTpmThreads)
+    EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmThreads, true)
+    EVG_TPM_ATTR(0, 16, uint8_t, 0, true, kTpmThreads)
+    EVG_TPM_ATTR(0, 16, uint16_t, 0, true, kTpmThreads)
+    EVG_TPM_ATTR(0, 16, uint8_t, 0, true, kTpmThreads, true)
+    EVG_TPM_ATTR(0, 16, uint16_t, 0, true, kTpmThreads, true)
 #undef EVG_TPM_ATTR
     switch (pick(t)) {
         case V_FAST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmThreads>, kTpmThreads, smem); break;
@@ -762,24 +806,38 @@ cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blo
     return e;
 }
 
+// The float32 observation vector is the default output; the wire row (EVG_OBS_WIRE) has its own instantiations.  The
+// compile-time DemoMap kernel with scripted agents AND wire rows is not instantiated: that combination takes the
+// run-time-sized kernel, which serves every configuration.
 cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, size_t smem, int max_grid, cudaStream_t stream)
 {
+    const bool agents = a.agent[0] != EVG_AGENT_EXTERNAL || a.agent[1] != EVG_AGENT_EXTERNAL;
+    const bool wire = a.obs_fmt == EVG_OBS_WIRE;
+    Variant v = pick(t);
+    if (v == V_FAST && agents && wire) {
+        v = V_GENERIC8;
+        threads = kTpmThreads;
+        smem = tpm_smem_bytes(t, threads);
+    }
     const int64_t nb = (a.n_envs + threads - 1) / threads;
     const unsigned grid = (unsigned)(nb < max_grid ? nb : max_grid);
-    const bool agents = a.agent[0] != EVG_AGENT_EXTERNAL || a.agent[1] != EVG_AGENT_EXTERNAL;
-    if (threads == kTpmSmallThreads) {
-        if (agents) evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads><<<grid, threads, smem, stream>>>(t, a);
-        else evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads><<<grid, threads, smem, stream>>>(t, a);
-        return cudaGetLastError();
+#define EVG_TPM_LAUNCH(...) evg_step_tpm_kernel<__VA_ARGS__><<<grid, threads, smem, stream>>>(t, a)
+    if (v == V_FAST && threads == kTpmSmallThreads) {
+        if (wire) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads, true);
+        else if (agents) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads);
+        else EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads);
+    } else if (v == V_FAST) {
+        if (wire) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmThreads, true);
+        else if (agents) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, true, kTpmThreads);
+        else EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmThreads);
+    } else if (v == V_GENERIC8) {
+        if (wire) EVG_TPM_LAUNCH(0, 16, uint8_t, 0, true, kTpmThreads, true);
+        else EVG_TPM_LAUNCH(0, 16, uint8_t, 0, true, kTpmThreads);
+    } else {
+        if (wire) EVG_TPM_LAUNCH(0, 16, uint16_t, 0, true, kTpmThreads, true);
+        else EVG_TPM_LAUNCH(0, 16, uint16_t, 0, true, kTpmThreads);
     }
-    switch (pick(t)) {
-        case V_FAST:
-            if (agents) evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, true, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a);
-            else evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a);
-            break;
-        case V_GENERIC8: evg_step_tpm_kernel<0, 16, uint8_t, 0, true, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
-        default: evg_step_tpm_kernel<0, 16, uint16_t, 0, true, kTpmThreads><<<grid, kTpmThreads, smem, stream>>>(t, a); break;
-    }
+#undef EVG_TPM_LAUNCH
     return cudaGetLastError();
 }
 

@@ -14,18 +14,19 @@ def shard_range(total_envs: int, rank: int, world_size: int):
 
 
 STAT_KEYS = ["episodes", "wins0", "wins1", "ties", "total_turns", "score0", "score1",
-             "status0", "status1", "status2", "status3", "env_turns"]
+             "status0", "status1", "status2", "status3", "env_turns", "fought_unit_slots"]
 
 
 def stats_to_vector(stats: dict):
     return [stats["episodes"], stats["wins"][0], stats["wins"][1], stats["ties"], stats["total_turns"],
-            stats["total_score"][0], stats["total_score"][1], *stats["status_count"], stats["env_turns"]]
+            stats["total_score"][0], stats["total_score"][1], *stats["status_count"], stats["env_turns"],
+            stats.get("fought_unit_slots", 0)]
 
 
 def vector_to_stats(v) -> dict:
     v = [int(x) for x in v]
     return {"episodes": v[0], "wins": [v[1], v[2]], "ties": v[3], "total_turns": v[4], "total_score": [v[5], v[6]],
-            "status_count": v[7:11], "env_turns": v[11]}
+            "status_count": v[7:11], "env_turns": v[11], "fought_unit_slots": v[12]}
 
 
 def gather_episode_stats(stats: dict, device=None) -> dict:

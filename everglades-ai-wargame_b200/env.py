@@ -23,6 +23,9 @@ def _torch():
     return torch
 
 
+OBS_FORMATS = {"f32": _capi.OBS_F32, "i16": _capi.OBS_I16, "wire": _capi.OBS_WIRE}
+
+
 class BatchedEvergladesEnv:
     """N Everglades matches stepped in lockstep by one CUDA launch per turn.
 
@@ -80,7 +83,8 @@ class BatchedEvergladesEnv:
         ptrs = (C.c_void_p * _capi.BIND_COUNT)(self._records.data_ptr(), self._health.data_ptr(), self._stats.data_ptr(),
                                                self._tables.data_ptr(), self._agents.data_ptr())
         _capi.check(self._lib.evg_bind(self._h, ptrs, _capi.BIND_COUNT))
-        self._host = None
+        self._host = {}
+        self._rows = {}
         self._is_reset = False
 
     # ------------------------------------------------------------------ plumbing
@@ -102,46 +106,86 @@ class BatchedEvergladesEnv:
     def launch_count(self) -> int:
         return int(self._lib.evg_launch_count(self._h))
 
+    def _to_int8_rows(self, actions, device):
+        """Any numeric [N,2,7,2] array -> int8 rows on `device`: astype(int) truncation toward zero (server.py:232),
+        then SATURATION into int8, so that ids beyond the int8 range stay out of range (no-op rows) instead of wrapping
+        into valid commands.  The one conversion both step() and step_host() use."""
+        torch = _torch()
+        shape = (self.num_envs, 2, _capi.MAX_ACTIONS, 2)
+        a = torch.as_tensor(actions)
+        if tuple(a.shape) != shape:
+            raise ValueError("actions must have shape %s, got %s" % (shape, tuple(a.shape)))
+        a = a.to(device)
+        if a.dtype == torch.int8:
+            return a
+        if a.is_floating_point():
+            a = a.trunc()
+        return a.clamp(-128, 127).to(torch.int8)
+
     def _as_actions(self, actions):
         torch = _torch()
         shape = (self.num_envs, 2, _capi.MAX_ACTIONS, 2)
         if isinstance(actions, torch.Tensor) and actions.dtype == torch.int8 and actions.device == self.device \
                 and tuple(actions.shape) == shape and actions.is_contiguous():
             return actions
-        a = torch.as_tensor(actions)
-        if tuple(a.shape) != shape:
-            raise ValueError("actions must have shape %s, got %s" % (shape, tuple(a.shape)))
-        # astype(int) truncation toward zero (server.py:232), then saturate into int8 (out-of-range rows are no-ops)
-        a = a.to(self.device)
-        if a.is_floating_point():
-            a = a.trunc()
-        self._actions.copy_(a.clamp(-128, 127).to(torch.int8))
+        self._actions.copy_(self._to_int8_rows(actions, self.device))
         return self._actions
 
-    # ------------------------------------------------------------------ reference-shaped API
-    def reset(self, mask=None):
-        """All matches (mask None) or the masked ones go back to the game_init state; returns obs."""
+    def _fmt(self, obs_format):
+        try:
+            return OBS_FORMATS[obs_format]
+        except KeyError:
+            raise ValueError("obs_format must be one of %s" % sorted(OBS_FORMATS))
+
+    def obs_rows(self, obs_format):
+        """The device tensor a non-float32 observation format is written into (allocated on first use):
+        'i16' int16 [N,2,L] (same layout as `obs`), 'wire' uint8 [N, row_bytes] (evgsim.wire / include/evgsim.h)."""
         torch = _torch()
+        fmt = self._fmt(obs_format)
+        if fmt == _capi.OBS_F32:
+            return self.obs
+        if obs_format not in self._rows:
+            if fmt == _capi.OBS_I16:
+                self._rows[obs_format] = torch.empty((self.num_envs, 2, self.obs_len), dtype=torch.int16, device=self.device)
+            else:
+                rb = int(self._lib.evg_obs_row_bytes(self._h, fmt))
+                self._rows[obs_format] = torch.empty((self.num_envs, rb), dtype=torch.uint8, device=self.device)
+        return self._rows[obs_format]
+
+    # ------------------------------------------------------------------ reference-shaped API
+    def reset(self, mask=None, obs_format="f32"):
+        """All matches (mask None) or the masked ones go back to the game_init state; returns obs (or, with another
+        obs_format, obs_rows(obs_format)).  A masked reset starts the slot's next episode (new combat tape)."""
+        torch = _torch()
+        fmt = self._fmt(obs_format)
         mptr = None
         if mask is not None:
+            if not self._is_reset:
+                raise RuntimeError("the first reset() must cover all matches (mask=None)")
             mask = torch.as_tensor(mask).to(self.device).ne(0).to(torch.uint8).contiguous()
             if tuple(mask.shape) != (self.num_envs,):
                 raise ValueError("mask must have shape (%d,)" % self.num_envs)
             mptr = C.c_void_p(mask.data_ptr())
-        _capi.check(self._lib.evg_reset(self._h, mptr, C.c_void_p(self.obs.data_ptr()), self._stream()))
+        rows = self.obs_rows(obs_format)
+        scratch = C.c_void_p(self.obs.data_ptr()) if fmt == _capi.OBS_I16 else None
+        _capi.check(self._lib.evg_reset_fmt(self._h, fmt, mptr, C.c_void_p(rows.data_ptr()), scratch, self._stream()))
         self._is_reset = True
-        return self.obs
+        return rows
 
-    def step(self, actions):
-        """One game turn for every match. Returns (obs, reward, done, info) — tensors, overwritten in place."""
+    def step(self, actions, obs_format="f32"):
+        """One game turn for every match. Returns (obs, reward, done, info) — tensors, overwritten in place.
+        obs_format 'wire' / 'i16': the observations come as obs_rows(obs_format) instead (lossless, fewer bytes)."""
         if not self._is_reset:
             raise RuntimeError("call reset() before step()")
         a = self._as_actions(actions)
-        _capi.check(self._lib.evg_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self.obs.data_ptr()),
-                                       C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
-                                       C.c_void_p(self.status.data_ptr()), C.c_void_p(self.scores.data_ptr()),
-                                       self._stream()))
-        return self.obs, self.reward, self.done, {"status": self.status, "scores": self.scores}
+        fmt = self._fmt(obs_format)
+        rows = self.obs_rows(obs_format)
+        scratch = C.c_void_p(self.obs.data_ptr()) if fmt == _capi.OBS_I16 else None
+        _capi.check(self._lib.evg_step_fmt(self._h, fmt, C.c_void_p(a.data_ptr()), C.c_void_p(rows.data_ptr()), scratch,
+                                           C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                           C.c_void_p(self.status.data_ptr()), C.c_void_p(self.scores.data_ptr()),
+                                           self._stream()))
+        return rows, self.reward, self.done, {"status": self.status, "scores": self.scores}
 
     def step_agents(self, agent0=_capi.AGENT_RANDOM, agent1=_capi.AGENT_RANDOM, actions=None, want_actions=False):
         """One turn with scripted opponents fused into the step kernel (evg_step_agents).
@@ -153,8 +197,10 @@ class BatchedEvergladesEnv:
             raise RuntimeError("call reset() before step()")
         ext = agent0 == _capi.AGENT_EXTERNAL or agent1 == _capi.AGENT_EXTERNAL
         aptr = None
+        rows_t = self._actions  # the tensor the kernels read external rows from and write generated rows into
         if ext:
-            aptr = C.c_void_p(self._as_actions(actions).data_ptr())
+            rows_t = self._as_actions(actions)
+            aptr = C.c_void_p(rows_t.data_ptr())
         elif (want_actions or not {int(agent0), int(agent1)} <= {_capi.AGENT_EXTERNAL, _capi.AGENT_RANDOM}
               or self._lib.evg_step_kernel_kind(self._h) == 0):
             # observation-driven agents, and any agent next to the warp-per-match kernel (small batches), run as
@@ -166,44 +212,61 @@ class BatchedEvergladesEnv:
                                               self._stream()))
         info = {"status": self.status, "scores": self.scores}
         if aptr is not None:
-            info["actions"] = self._actions
+            info["actions"] = rows_t
         return self.obs, self.reward, self.done, info
 
     # ------------------------------------------------------------------ host-buffer path (end-to-end)
-    def host_buffers(self):
-        """Pinned host arrays for step_host: actions int8[N,2,7,2] in; obs, reward, done out."""
-        if self._host is None:
+    def host_buffers(self, obs_format="f32"):
+        """Pinned host arrays for step_host: actions int8[N,2,7,2] in; obs (in `obs_format`), reward, done out.
+        They are allocated by evgsim.hostmem (page-locked, on the NUMA node next to this GPU where the kernel allows)."""
+        if obs_format not in self._host:
             torch = _torch()
+            from . import hostmem
+            fmt = self._fmt(obs_format)
             N = self.num_envs
-            self._host = {
-                "actions": torch.zeros((N, 2, _capi.MAX_ACTIONS, 2), dtype=torch.int8).pin_memory(),
-                "obs": torch.empty((N, 2, self.obs_len), dtype=torch.float32).pin_memory(),
-                "reward": torch.empty((N, 2), dtype=torch.float32).pin_memory(),
-                "done": torch.empty((N,), dtype=torch.uint8).pin_memory(),
+            dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            if fmt == _capi.OBS_F32:
+                obs = hostmem.pinned_empty((N, 2, self.obs_len), torch.float32, dev)
+            elif fmt == _capi.OBS_I16:
+                obs = hostmem.pinned_empty((N, 2, self.obs_len), torch.int16, dev)
+            else:
+                obs = hostmem.pinned_empty((N, int(self._lib.evg_obs_row_bytes(self._h, fmt))), torch.uint8, dev)
+            first = next(iter(self._host.values()), None)
+            self._host[obs_format] = {
+                "actions": first["actions"] if first else hostmem.pinned_empty((N, 2, _capi.MAX_ACTIONS, 2), torch.int8, dev).zero_(),
+                "obs": obs,
+                "reward": first["reward"] if first else hostmem.pinned_empty((N, 2), torch.float32, dev),
+                "done": first["done"] if first else hostmem.pinned_empty((N,), torch.uint8, dev),
             }
-        return self._host
+        return self._host[obs_format]
 
-    def step_host(self, actions=None, sync=True):
-        """Same turn through HOST memory: H2D actions, step, D2H obs/reward/done (evg_step_host).
+    def step_host(self, actions=None, sync=True, obs_format="f32"):
+        """Same turn through HOST memory: H2D actions, step, D2H obs/reward/done (evg_step_host_fmt).
 
         `actions`: None (use host_buffers()['actions'] as filled by the caller) or an array copied into
-        it.  Returns the pinned host tensors (valid after the stream is synchronised; sync=True does it).
+        it.  obs_format: 'f32' (the reference's vector, 840 B per match on DemoMap), 'i16' (same layout, 420 B) or
+        'wire' (one packed 128-byte row per match that also carries reward and done; evgsim.wire.expand rebuilds the
+        float32 vector exactly).  Returns the pinned host tensors (valid after the stream is synchronised; sync=True
+        does it).
         """
         if not self._is_reset:
             raise RuntimeError("call reset() before step()")
         torch = _torch()
-        hb = self.host_buffers()
+        fmt = self._fmt(obs_format)
+        hb = self.host_buffers(obs_format)
         src = hb["actions"]
         if actions is not None:
             if isinstance(actions, torch.Tensor) and actions.dtype == torch.int8 and actions.device.type == "cpu" \
                     and actions.is_pinned() and actions.is_contiguous() and tuple(actions.shape) == tuple(src.shape):
                 src = actions  # already page-locked: DMA straight from the caller's buffer
             else:
-                src.copy_(torch.as_tensor(actions).to(torch.int8).reshape(src.shape))
-        _capi.check(self._lib.evg_step_host(
-            self._h, C.c_void_p(src.data_ptr()), C.c_void_p(hb["obs"].data_ptr()),
+                src.copy_(self._to_int8_rows(actions, "cpu"))
+        rows = self.obs_rows(obs_format)
+        scratch = C.c_void_p(self.obs.data_ptr()) if fmt == _capi.OBS_I16 else None
+        _capi.check(self._lib.evg_step_host_fmt(
+            self._h, fmt, C.c_void_p(src.data_ptr()), C.c_void_p(hb["obs"].data_ptr()),
             C.c_void_p(hb["reward"].data_ptr()), C.c_void_p(hb["done"].data_ptr()),
-            C.c_void_p(self._actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+            C.c_void_p(self._actions.data_ptr()), C.c_void_p(rows.data_ptr()), scratch,
             C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), self._stream()))
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
@@ -212,8 +275,8 @@ class BatchedEvergladesEnv:
     def h2d_bytes_per_step(self) -> int:
         return self.num_envs * int(self.layout.action_bytes)
 
-    def d2h_bytes_per_step(self) -> int:
-        return self.num_envs * (2 * self.obs_len * 4 + 2 * 4 + 1)
+    def d2h_bytes_per_step(self, obs_format="f32") -> int:
+        return self.num_envs * (int(self._lib.evg_obs_row_bytes(self._h, self._fmt(obs_format))) + 2 * 4 + 1)
 
     # ------------------------------------------------------------------ scripted agents on the device
     def random_actions(self, player=-1, out=None):
@@ -292,19 +355,25 @@ class BatchedEvergladesEnv:
         _capi.check(self._lib.evg_episode_stats(self._h, C.byref(st), self._stream()))
         return {"episodes": st.episodes, "wins": [st.wins[0], st.wins[1]], "ties": st.ties,
                 "total_turns": st.total_turns, "total_score": [st.total_score[0], st.total_score[1]],
-                "status_count": [st.status_count[i] for i in range(4)], "env_turns": st.env_turns}
+                "status_count": [st.status_count[i] for i in range(4)], "env_turns": st.env_turns,
+                "fought_unit_slots": st.fought_unit_slots}
 
 
 class EvergladesEnv:
     """Drop-in for ``gym_everglades.envs.EvergladesEnv`` (env.py:13-116), one match on the GPU.
 
-    Same attributes (env.py:17-28), ``reset(**kwargs) -> {pid: float64[105]}`` and
-    ``step({pid: array[k,2]}) -> (obs, reward, done, {})`` with the reference's types and error
-    behaviour: AssertionError for != 2 players (env.py:87) or != 2 action columns (server.py:226),
-    IndexError for group ids outside [-12, 11] and player-1 node ids outside [-12, 11]
-    (server.py:92,235; negative ids wrap like Python lists).  ``render``/``close`` are no-ops (the
-    pyglet viewer is out of scope).  Combat randomness comes from the Philox tape keyed on `seed`.
+    Same attributes (env.py:17-28, with ``observation_space`` a Box[105] and ``action_space`` a Tuple of
+    (Discrete 12, Discrete 12) x 7 — gym's classes when gym/gymnasium is installed, stand-ins with the same attributes
+    otherwise), ``reset(**kwargs) -> {pid: float64[105]}`` and ``step({pid: array[k,2]}) -> (obs, reward, done, {})``
+    with the reference's types and error behaviour: AssertionError for != 2 players (env.py:87) or != 2 action columns
+    (server.py:226), IndexError for group ids outside [-12, 11] and player-1 node ids outside [-12, 11]
+    (server.py:92,235; negative ids wrap like Python lists).  ``render``/``close`` are no-ops (the pyglet viewer is out
+    of scope).  Combat randomness comes from the Philox tape keyed on (`seed`, match id, EPISODE, ...): the simulator is
+    kept across ``reset()`` calls and every reset starts the next episode of the slot, so successive episodes draw
+    different combat targets, like the reference's global numpy stream that carries on across resets.
     """
+
+    metadata = {"render.modes": ["human"]}
 
     def __init__(self, device=0, seed=0):
         self.num_turns = 150
@@ -313,21 +382,24 @@ class EvergladesEnv:
         self.num_nodes = 11
         self.num_actions_per_turn = 7
         self.unit_classes = list(UNIT_CLASSES)
-        self.action_space = tuple((self.num_groups, self.num_nodes + 1) for _ in range(self.num_actions_per_turn))
-        self.observation_space = self._build_observation_space()
+        from .spaces import space_classes
+        Box, Discrete, Tuple = space_classes()
+        self.action_space = Tuple((Discrete(self.num_groups), Discrete(self.num_nodes + 1)) * self.num_actions_per_turn)  # env.py:25
+        self.observation_space = self._build_observation_space(Box)
         self.viewer = None
         self._device, self._seed = device, seed
         self._env = None
+        self._env_key = None
 
-    def _build_observation_space(self):
-        """(low, high) bounds as env.py:124-143 declares them (controlState of bases exceeds them: SURVEY A.5)."""
+    def _build_observation_space(self, Box):
+        """Box bounds as env.py:124-143 declares them (controlState of bases exceeds them: SURVEY A.5)."""
         group_low = np.array([1, 0, 0, 0, 0])
         group_high = np.array([self.num_nodes, len(self.unit_classes), 100, 1, self.num_units])
         cp_low = np.array([0, 0, -100, -1])
         cp_high = np.array([1, 1, 100, self.num_units])
         low = np.concatenate([[1], np.tile(cp_low, self.num_nodes), np.tile(group_low, self.num_groups)])
         high = np.concatenate([[self.num_turns + 1], np.tile(cp_high, self.num_nodes), np.tile(group_high, self.num_groups)])
-        return low, high
+        return Box(low=low.astype(np.float32), high=high.astype(np.float32))
 
     def reset(self, **kwargs):
         self.players = kwargs.get("players")
@@ -341,17 +413,21 @@ class EvergladesEnv:
         for p in self.pks:
             assert p in (0, 1), "Given player number not included in map configuration file starting locations"
         cfg = load_config(config_dir, map_file, unit_file, kwargs.get("setup_file", "GameSetup.json"))
-        if self._env is not None:
-            self._env.close()
-        self._env = BatchedEvergladesEnv(1, device=self._device, seed=self._seed, config=cfg,
-                                         auto_reset=_capi.AUTORESET_OFF,
-                                         env_id_offset=kwargs.get("env_id", 0))
+        key = (bytes(cfg), int(kwargs.get("env_id", 0)))
+        if self._env is None or key != self._env_key:
+            # first game, or other config files than last time: a new simulator (episode counter back to 0)
+            if self._env is not None:
+                self._env.close()
+            self._env = BatchedEvergladesEnv(1, device=self._device, seed=self._seed, config=cfg,
+                                             auto_reset=_capi.AUTORESET_OFF, env_id_offset=key[1])
+            self._env_key = key
+            obs = self._env.reset()
+        else:
+            obs = self._env.reset(mask=[1])  # same game files: next episode of the same slot, nothing reallocated
         self.num_nodes = self._env.num_nodes
         self.num_turns = self._env.num_turns
         self.num_units = self._env.num_units
-        obs = self._env.reset()
         return self._obs_dict(obs)
-
     def _obs_dict(self, obs):
         o = obs[0].to("cpu").numpy().astype(np.float64)
         return {p: o[p].copy() for p in self.players}
@@ -397,3 +473,4 @@ class EvergladesEnv:
         if self._env is not None:
             self._env.close()
             self._env = None
+            self._env_key = None

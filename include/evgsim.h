@@ -153,6 +153,9 @@ typedef struct EvgEpisodeStats {
     int64_t total_score[2];  /* sum of final scores */
     int64_t status_count[4]; /* histogram of EVG_STATUS_* at episode end */
     int64_t env_turns;       /* all match-turns stepped since creation / last clear */
+    int64_t fought_unit_slots; /* unit slots of the groups that took part in combat, summed over all match-turns
+                                  stepped (finished matches or not): 16 B of fp64 health traffic each, the variable
+                                  term of the step's algorithmic bytes (server.py:516-566) */
 } EvgEpisodeStats;
 
 typedef struct EvgSim EvgSim; /* opaque */
@@ -190,6 +193,31 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream);
 int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done,
              uint8_t* d_status, int32_t* d_scores, void* stream);
 
+/*
+ * Observation formats.  EVG_OBS_F32 is the reference's vector (env.py:158-171) as float32.  The other two carry the SAME
+ * information losslessly in fewer bytes, for consumers behind a narrow link (the host over PCIe: evg_step_host_fmt):
+ *
+ *   EVG_OBS_I16   int16 [n_envs][2][obs_len], same layout as the float32 vector (every entry is an integer in
+ *                 [-32768, 32767]: turn <= 65535 is checked at create time against this format on use).
+ *   EVG_OBS_WIRE  one packed row per match, evg_obs_row_bytes() bytes = round_up(4 + 4*n_nodes + 72 + 8, 16)
+ *                 (128 on DemoMap: one cache line), little endian:
+ *        [0:2)  turn uint16 (obs[0], server.py:432)    [2] done uint8    [3] status uint8 (EVG_STATUS_*)
+ *        [4 + 4*(x-1) ...) for node id x = 1..n_nodes: controlState int16 (raw sign, server.py:444), units of player 0's
+ *                 groups listed at the node uint8, units of player 1's groups uint8 (server.py:446-449; a viewer's
+ *                 "opponent units" entry is the other player's byte)
+ *        [G = 4 + 4*n_nodes + 3*(12*p + g) ...) group g of player p: byte 0 = location in REAL node numbering [0:6) |
+ *                 moving << 6 (server.py:477,489), byte 1 = avg health (server.py:491), byte 2 = units alive (:480)
+ *        [G + 72 : G + 80)  the step's rewards, float32[2] (env.py:37-60)
+ *        zero padding to the row size.
+ *   What the float32 vector holds besides is static: the nodes' DEFENSE/OBSERVE flags, the groups' unit types, and
+ *   player 1's node numbering (server.py:437-439, 476) — a function of EvgConfig alone.  evgsim.wire.expand() /
+ *   INTEGRATION.md give the expansion; tests/test_gpu_wire.py checks expand(wire) == float32 observations bit for bit.
+ */
+#define EVG_OBS_F32 0
+#define EVG_OBS_I16 1
+#define EVG_OBS_WIRE 2
+#define EVG_WIRE_NODE0 4 /* byte offset of node 1's entry in a wire row */
+
 /* where a player's action rows come from in evg_step_agents */
 #define EVG_AGENT_EXTERNAL 0 /* the caller's rows in d_actions */
 #define EVG_AGENT_RANDOM 1   /* on-device random_actions agent (agents/State_Machine/random_actions.py:38-46) */
@@ -211,6 +239,20 @@ int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_a
  * the kernel of the next; results are those of evg_step. */
 int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done,
                   int8_t* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, void* stream);
+
+/* Bytes per match of an observation format (0 for an unknown format or NULL sim). */
+int evg_obs_row_bytes(const EvgSim* sim, int32_t format);
+
+/* evg_reset / evg_step / evg_step_host with the observation output in `format` (EVG_OBS_*); with EVG_OBS_F32 they ARE
+ * those calls.  d_rows / h_rows: n_envs rows of evg_obs_row_bytes(sim, format).  EVG_OBS_WIRE rows are written by the
+ * step kernel itself (no float32 observations are produced at all); EVG_OBS_I16 needs a caller-provided float32
+ * scratch d_obs_f32 [n_envs][2][obs_len] that the step writes and a conversion kernel narrows.  In evg_step_host_fmt
+ * h_reward / h_done may be NULL with EVG_OBS_WIRE (the row carries them). */
+int evg_reset_fmt(EvgSim* sim, int32_t format, const uint8_t* d_mask, void* d_rows, float* d_obs_f32, void* stream);
+int evg_step_fmt(EvgSim* sim, int32_t format, const int8_t* d_actions, void* d_rows, float* d_obs_f32, float* d_reward,
+                 uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream);
+int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void* h_rows, float* h_reward, uint8_t* h_done,
+                      int8_t* d_actions, void* d_rows, float* d_obs_f32, float* d_reward, uint8_t* d_done, void* stream);
 
 /* Array-of-structs snapshot <-> resident layout, matches [first, first+count).  d_states is a
  * DEVICE array of EvgEnvState (the caller copies it to/from the host). */
@@ -249,9 +291,9 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
 int evg_shape_reward(EvgSim* sim, int32_t mode, const float* d_reward, const uint8_t* d_done, const float* d_obs, float* d_out,
                      void* stream);
 
-/* Which step kernel evg_create() selected: 0 = a warp per match (small batches), 1 = a thread per match,
- * 2 = a lane pair per match.  Scripted agents are fused into kernels 1 and 2 only; with
- * kernel 0 evg_step_agents() needs a non-NULL d_actions to pass the generated rows through.  -1 if sim is NULL. */
+/* Which step kernel evg_create() selected: 0 = a warp per match (small batches), 1 = a thread per match
+ * (DESIGN.md section 4).  Scripted agents are fused into kernel 1 only; with kernel 0 evg_step_agents() needs
+ * a non-NULL d_actions to pass the generated rows through.  -1 if sim is NULL. */
 int evg_step_kernel_kind(const EvgSim* sim);
 
 /* Number of kernels this library has launched since creation (bench.py's gpu_launches). */

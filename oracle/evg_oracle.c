@@ -243,6 +243,16 @@ void evo_reset(const EvgConfig* c, EvgEnvState* s, int32_t episode)
     capture(c, s, &L); /* server.py:206, current_turn == 0 */
 }
 
+/* Unit slots of the groups that took part in combat, summed over every evo_step of this thread: the
+ * checker of the device counter EvgEpisodeStats.fought_unit_slots (16 B of health traffic per slot). */
+static __thread int64_t g_fought_slots = 0;
+int64_t evo_fought_slots(int clear)
+{
+    int64_t v = g_fought_slots;
+    if (clear) g_fought_slots = 0;
+    return v;
+}
+
 /* ------------------------------------------------------------------ combat, server.py:503-654 */
 static void combat(const EvgConfig* c, EvgEnvState* s, NodeLists* L, uint64_t seed, uint64_t env)
 {
@@ -258,6 +268,8 @@ static void combat(const EvgConfig* c, EvgEnvState* s, NodeLists* L, uint64_t se
                 }
             }
         if (!(npg[0] > 0 && npg[1] > 0)) continue; /* server.py:539 */
+        for (int p = 0; p < NP; ++p)
+            for (int k = 0; k < npg[p]; ++k) g_fought_slots += c->group_size[p][pg[p][k]];
 
         /* infliction[pid][uid] += damage, server.py:549-566 */
         int infl[NP][NG * MU];

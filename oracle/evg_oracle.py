@@ -56,6 +56,8 @@ def lib():
         L.evo_agent_swarm.restype = None
         L.evo_philox.argtypes = [P, P, P]
         L.evo_philox.restype = None
+        L.evo_fought_slots.argtypes = [C.c_int]
+        L.evo_fought_slots.restype = C.c_int64
         assert L.evo_sizeof_config() == C.sizeof(_capi.EvgConfig)
         assert L.evo_sizeof_state() == C.sizeof(_capi.EvgEnvState)
         _LIB = L
@@ -165,6 +167,11 @@ def run_random(cfg, seed, first, count, n_turns):
     chk, eps = C.c_double(0), C.c_int64(0)
     n = lib().evo_run_random(C.byref(cfg), int(seed), int(first), int(count), int(n_turns), C.byref(chk), C.byref(eps))
     return int(n), chk.value, eps.value
+
+
+def fought_slots(clear=False):
+    """Unit slots of the groups that fought in this thread's evo_step calls so far (checks the device counter)."""
+    return int(lib().evo_fought_slots(1 if clear else 0))
 
 
 def list_rank(state_rec):

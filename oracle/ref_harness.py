@@ -1,10 +1,11 @@
-"""Drive the UNMODIFIED reference (server.py + everglades_env.py) under the random tape.
+"""Drive the UNMODIFIED reference (server.py + everglades_env.py) under the random tape, and time it.
 
-TEST INFRASTRUCTURE ONLY.  Works only where ``/root/reference`` exists (the
-build container); it is used by ``tests/golden/gen_golden.py`` to produce the
-committed golden trajectories and by ``tests/test_oracle_vs_reference.py``
-(skipped when the reference is absent).  Nothing here travels to the GPU box
-except the fixtures it generated.
+TEST INFRASTRUCTURE ONLY.  The reference is read from ``/root/reference`` where that exists (the
+build container) and otherwise from ``oracle/_ref/``, where ``oracle/stage_ref.py`` staged the same
+files byte for byte so that they reach the GPU box.  Used by ``tests/golden/gen_golden.py`` to
+produce the committed golden trajectories, by ``tests/test_oracle_vs_reference.py`` (skipped when
+neither copy is present) and by bench.py's ``cpu_baseline`` / ``--impl reference`` legs
+(``time_reference``: the real Python server on the box's host cores).
 
 What is imported from the reference, untouched:
   * ``everglades_server.server.EvergladesGame``   (server.py:11)
@@ -24,7 +25,18 @@ import numpy as np
 
 from . import tape
 
-REFERENCE_ROOT = os.environ.get("EVG_REFERENCE_ROOT", "/root/reference")
+def _pick_root() -> str:
+    env = os.environ.get("EVG_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for root in ("/root/reference", staged):
+        if os.path.isfile(os.path.join(root, "everglades-server", "everglades_server", "server.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
@@ -204,3 +216,65 @@ def run_reference_game(seed: int, env_id: int, actions: np.ndarray, map_file: st
     if keep_log:
         out["log"] = log
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Timing the unmodified reference (bench.py cpu_baseline kind "reference"; SURVEY.md 8d "CPU baseline")
+# ------------------------------------------------------------------------------------------------
+def _time_worker(args):
+    """One process: random_actions-vs-random_actions matches through the reference's own EvergladesEnv.reset/step
+    (game_turn + both players' board_state/player_state, server.py:211-279,382-501) for about `seconds`; the action
+    arrays are pre-drawn, the server draws its combat targets from its own global numpy stream (nothing patched).
+    Returns (env_turns, seconds spent inside reset/step)."""
+    import io
+    import time
+    import contextlib
+
+    seconds, seed = args
+    _, EvergladesEnv = import_reference()
+    import gym_everglades.envs.everglades_env as envmod
+    envmod.EvergladesRenderer = lambda game: None  # the viewer is not on the step path (pyglet absent)
+    rng = np.random.default_rng(seed)
+    pool = np.zeros((256, 2, 7, 2), dtype=np.int64)
+    for k in range(256):
+        for p in range(2):  # random_actions.py:38-46: 7 distinct groups, 7 distinct nodes
+            pool[k, p, :, 0] = rng.permutation(12)[:7]
+            pool[k, p, :, 1] = rng.permutation(np.arange(1, 12))[:7]
+    np.random.seed(seed)
+    env = EvergladesEnv()
+    kw = dict(players={0: None, 1: None}, config_dir=CONFIG_DIR, map_file=CONFIG_DIR + "DemoMap.json",
+              unit_file=CONFIG_DIR + "UnitDefinitions.json", output_dir="/tmp/", pnames={0: "a", 1: "b"}, debug=False)
+    turns, spent, k = 0, 0.0, 0
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        while spent < seconds:
+            t0 = time.perf_counter()
+            env.reset(**kw)
+            done = 0
+            while not done:
+                a = pool[k & 255]
+                k += 1
+                _, _, done, _ = env.step({0: a[0], 1: a[1]})
+                turns += 1
+            spent += time.perf_counter() - t0
+    return turns, spent
+
+
+def time_reference(seconds: float = 10.0, procs: int | None = None):
+    """env-turns/s of the unmodified Python reference on `procs` host processes (default: one per CPU), each playing
+    whole matches for about `seconds`.  Returns (rate_all, procs, rate_one_process, sample description)."""
+    import multiprocessing as mp
+    import time
+
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_time_worker, [(seconds, 1000 + i) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    turns = sum(r[0] for r in res)
+    rate_all = sum(r[0] / r[1] for r in res)       # processes run side by side: aggregate of per-process rates
+    rate_one = res[0][0] / res[0][1]
+    sample = ("%d processes x ~%.0f s of whole random_actions-vs-random_actions matches through the unmodified "
+              "EvergladesEnv.reset/step (%d env-turns in total, %.1f s wall incl. process start)" % (procs, seconds, turns, wall))
+    return rate_all, procs, rate_one, sample

@@ -24,7 +24,8 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     stats = {"episodes": 10 + rank, "wins": [3 + rank, 4], "ties": 3, "total_turns": 1500 * (rank + 1),
-             "total_score": [100, 200 * rank], "status_count": [0, 9 + rank, 1, 0], "env_turns": 1000 * (rank + 1)}
+             "total_score": [100, 200 * rank], "status_count": [0, 9 + rank, 1, 0], "env_turns": 1000 * (rank + 1),
+             "fought_unit_slots": 500 + 7 * rank}
     total = evd.gather_episode_stats(stats)
     if rank == 0:
         torch.save(total, out)
@@ -40,10 +41,10 @@ def test_gather_episode_stats_gloo_world2(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     total = torch.load(out)
     assert total == {"episodes": 21, "wins": [7, 8], "ties": 6, "total_turns": 4500, "total_score": [200, 200],
-                     "status_count": [0, 19, 2, 0], "env_turns": 3000}
+                     "status_count": [0, 19, 2, 0], "env_turns": 3000, "fought_unit_slots": 1007}
 
 
 def test_gather_without_process_group_is_identity():
     stats = {"episodes": 1, "wins": [1, 0], "ties": 0, "total_turns": 150, "total_score": [5, 6],
-             "status_count": [0, 1, 0, 0], "env_turns": 150}
+             "status_count": [0, 1, 0, 0], "env_turns": 150, "fought_unit_slots": 96}
     assert evd.gather_episode_stats(stats) == stats

@@ -30,7 +30,7 @@ def write_configs(tmp_path, budget, turn_limit=60, bonus=300):
     return str(tmp_path)
 
 
-@pytest.mark.parametrize("kernel", ["pair", "tpm"])
+@pytest.mark.parametrize("kernel", ["tpm"])
 @pytest.mark.parametrize("budget", [60, 100, 120, 180, 192, 12])
 def test_other_map_units_and_budgets(tmp_path, budget, kernel, monkeypatch):
     monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
@@ -78,7 +78,7 @@ def write_ring32(tmp_path):
     return str(tmp_path)
 
 
-@pytest.mark.parametrize("kernel", ["tpm", "pair", "warp"])
+@pytest.mark.parametrize("kernel", ["tpm", "warp"])
 def test_largest_map_32_nodes(tmp_path, kernel, monkeypatch):
     """32 nodes: 352-byte records (more than one 8-byte word per lane), 189-value observations, the byte-array
     variant of the random agent, run-time-sized kernels."""
@@ -114,7 +114,7 @@ def test_largest_map_32_nodes(tmp_path, kernel, monkeypatch):
     assert env.episode_stats()["episodes"] >= 2 * n
 
 
-@pytest.mark.parametrize("kernel", ["tpm", "pair", "warp"])
+@pytest.mark.parametrize("kernel", ["tpm", "warp"])
 def test_simulators_of_different_configurations_coexist(tmp_path, kernel, monkeypatch):
     """The step kernels are shared by every simulator of a process; one that needs less shared memory, created
     later, must not take the opt-in away from an earlier one that needs more (32-node map vs 7-node map vs DemoMap)."""

@@ -111,6 +111,7 @@ def run_against_oracle(evg, eo, cfg, n, turns, seed, first, make_actions, auto_r
     ora = eo.OracleBatch(cfg, n, seed=seed, first=first)
     assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
     ndone = 0
+    eo.fought_slots(clear=True)
     for t in range(turns):
         acts = make_actions(ora.states)
         obs, rew, done, info = env.step(acts)
@@ -124,6 +125,8 @@ def run_against_oracle(evg, eo, cfg, n, turns, seed, first, make_actions, auto_r
         ndone += int(odone.sum())
         if (t + 1) % state_every == 0 or t == turns - 1:
             assert_states_equal(env.get_state(), ora.states, where)
+    # the device's count of unit slots that fought (the health term of bench.py's algorithmic bytes)
+    assert env.episode_stats()["fought_unit_slots"] == eo.fought_slots(), "fought_unit_slots"
     return env, ora, ndone
 
 
@@ -267,7 +270,7 @@ def test_step_host_equals_step(evg, eo, cfg):
     assert env.h2d_bytes_per_step() == n * 28 and env.d2h_bytes_per_step() == n * (840 + 8 + 1)
 
 
-@pytest.mark.parametrize("kernel", ["pair", "tpm", "tpm128", "warp"])
+@pytest.mark.parametrize("kernel", ["tpm", "tpm128", "warp"])
 def test_every_step_kernel_matches_oracle(evg, eo, cfg, monkeypatch, kernel):
     """The step kernels (two lanes per match / one thread per match in 32- and in 128-thread CTAs / one warp per match)
     stay selectable (EVG_STEP_KERNEL, EVG_TPM_SMALL_MAX) for A/B profiling; each must match the oracle, with auto-reset
