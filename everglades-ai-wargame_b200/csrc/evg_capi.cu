@@ -493,6 +493,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.records = (uint32_t*)sim->bound[EVG_BIND_RECORDS];
     a.health = (double*)sim->bound[EVG_BIND_HEALTH];
     a.stats = (unsigned long long*)sim->bound[EVG_BIND_STATS];
+    a.agent_state = (uint2*)sim->bound[EVG_BIND_AGENTS];
     a.actions = d_actions;
     a.obs = (float*)d_obs;
     a.obs_fmt = obs_fmt;
@@ -509,6 +510,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
         a.health += first * t.health_slots;
         if (a.actions) a.actions += first * 2 * EVG_MAX_ACTIONS * 2;
         if (a.actions_out) a.actions_out += first * 2 * EVG_MAX_ACTIONS * 2;
+        a.agent_state += first * 2;
         a.obs = (float*)((char*)d_obs + first * (obs_fmt == EVG_OBS_WIRE ? evg::wire_bytes(t.n_nodes) : 2 * t.obs_len * 4));
         a.reward += first * 2;
         a.done += first;
@@ -547,13 +549,13 @@ int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_a
         if (ag[p] < EVG_AGENT_EXTERNAL || ag[p] > EVG_AGENT_SWARM) return fail(EVG_E_ARG, "unknown agent id %d for player %d", ag[p], p);
         any_ext |= ag[p] == EVG_AGENT_EXTERNAL;
         any_scripted |= ag[p] != EVG_AGENT_EXTERNAL;
-        fusable &= ag[p] == EVG_AGENT_EXTERNAL || ag[p] == EVG_AGENT_RANDOM;
+        fusable &= ag[p] != EVG_AGENT_RANDOM || sim->cfg.n_nodes <= evg::kAgentMaxNodes;  // the register-only random agent
     }
     if (any_ext && !d_actions) return fail(EVG_E_ARG, "evg_step_agents: d_actions is required for EVG_AGENT_EXTERNAL players");
-    const bool fused = fusable && sim->use_tpm && sim->cfg.n_nodes <= evg::kAgentMaxNodes;
+    const bool fused = fusable && sim->use_tpm;
     if (!any_scripted || fused)
         return step_impl(sim, agent_p0, agent_p1, d_actions, any_scripted ? d_actions : nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
-    // not fusable (warp-per-match kernel selected, or a map too large for the register-only agent): agent
+    // not fusable (warp-per-match kernel selected, or a map too large for the register-only random agent): agent
     // kernel(s) into d_actions, then the plain step
     if (!d_actions) return fail(EVG_E_ARG, "evg_step_agents: d_actions is required when the agents cannot be fused into the step kernel");
     if ((rc = evg_agents(sim, agent_p0, agent_p1, d_actions, stream))) return rc;

@@ -124,6 +124,7 @@ struct StepArgs {
     const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
     int64_t env_first;        // thread-per-match kernel: this launch covers matches [env_first, env_first + n_envs) of the
                               // simulator (all pointers above are already offset); 0 for a whole-batch launch
+    uint2* agent_state;       // per (match, player) state of the observation-driven scripted agents (bind slot EVG_BIND_AGENTS)
     int32_t obs_fmt;          // EVG_OBS_F32: `obs` is float32[n][2][obs_len]; EVG_OBS_WIRE: packed rows of wire_bytes(n_nodes)
 };
 
@@ -209,6 +210,67 @@ __device__ __forceinline__ void agent_random_rows(uint32_t env_global, uint32_t 
             node = (uint32_t)(np >> (4 * k)) & 15u;
         }
         rows[k] = ((uint32_t)(gp >> (4 * k)) & 15u) | node << 8;
+    }
+}
+
+// base_rushV1.get_action (agents/State_Machine/base_rush_v1.py:62-111) for player p.  w0_of(L) returns word 0 of group
+// lane L's record (location [0:6), moving bit 21); st.x = {bit0 started, group_num [4:8), node_num [8:16)}, 0 = a fresh
+// agent.  Same function as evo_agent_base_rush (oracle/evg_oracle.c), which is pinned to games of the reference's class.
+template <typename W0>
+__device__ __forceinline__ void agent_base_rush_rows(const Tables& T, W0 w0_of, uint2& st, int p, uint32_t rows[EVG_MAX_ACTIONS])
+{
+    const bool started = st.x & 1u;
+    uint32_t gnum = started ? (st.x >> 4) & 15u : 1u, nnum = started ? (st.x >> 8) & 255u : 2u;
+#pragma unroll
+    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) {
+        rows[k] = 0;
+        if (started) {  // the first call only blows the turn (:73-76)
+            const uint32_t loc = w0_of(p * EVG_NUM_GROUPS + k) & W0_LOC_MASK;  // GROUP k's location (:86-88)
+            const uint32_t own = p ? (uint32_t)T.p1_map[loc] : loc;
+            if (own != T.base_own[p]) {
+                rows[k] = gnum | nnum << 8;
+                gnum = gnum + 1 == EVG_NUM_GROUPS ? 0u : gnum + 1;
+                if (gnum == 0) nnum = nnum % (uint32_t)T.n_nodes + 1u;
+            }
+        }
+    }
+    st.x = 1u | gnum << 4 | nnum << 8;
+}
+
+// SwarmAgent.get_action (agents/State_Machine/swarm_agent.py:79-102) for player p; st.y = the agent's attack list as
+// nibbles (0 = a fresh agent), shuffled in place every turn by numpy's Fisher-Yates on the tape (domain 2).
+template <typename W0>
+__device__ __forceinline__ void agent_swarm_rows(const Tables& T, W0 w0_of, uint2& st, uint32_t env_global, uint32_t turn, uint32_t episode,
+                                                 int p, uint32_t rows[EVG_MAX_ACTIONS])
+{
+    uint32_t lst = st.y ? st.y : 0xBA875421u;  // ATTACK_LIST [1,2,4,5,7,8,10,11], :24
+    uint32_t w[4];
+    philox4x32_10(env_global, turn, (uint32_t)p, 2u | episode << 8, T.seed_lo, T.seed_hi, w);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {  // np.random.shuffle: i = 7..1, j uniform in [0, i]
+        const int ii = 7 - k;
+        const uint32_t h = (k & 1) ? w[k >> 1] >> 16 : w[k >> 1] & 0xFFFFu;
+        const int j = (int)((h * (uint32_t)(ii + 1)) >> 16);
+        const uint32_t d = ((lst >> (4 * ii)) ^ (lst >> (4 * j))) & 15u;
+        lst ^= d << (4 * ii) | d << (4 * j);
+    }
+    st.y = lst;
+#pragma unroll
+    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) rows[k] = 0u | 1u << 8;  // default rows [0, 1], :81-82
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t x = (lst >> (4 * k)) & 15u;
+        const uint32_t w0 = w0_of(p * EVG_NUM_GROUPS + (int)x);
+        if (n < EVG_MAX_ACTIONS && !(w0 & W0_MOVING)) {
+            const uint32_t loc = w0 & W0_LOC_MASK;
+            const uint32_t own = p ? (uint32_t)T.p1_map[loc] : loc;
+            const uint32_t row = x | (uint32_t)T.maxnb_own[p][own] << 8;
+#pragma unroll
+            for (int q = 0; q < EVG_MAX_ACTIONS; ++q)
+                if (q == n) rows[q] = row;
+            ++n;
+        }
     }
 }
 #endif

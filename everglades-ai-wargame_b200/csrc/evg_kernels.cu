@@ -728,59 +728,12 @@ __global__ void evg_agents_kernel(const __grid_constant__ Tables T, const uint32
     uint32_t rows[EVG_MAX_ACTIONS];
     if (kind == EVG_AGENT_RANDOM) {  // maps of <= 15 nodes (checked by the host)
         agent_random_rows(T.env_base + (uint32_t)env, turn, episode, p, T.n_nodes, T.seed_lo, T.seed_hi, rows);
-    } else if (kind == EVG_AGENT_BASE_RUSH) {
-        // base_rushV1.get_action, agents/State_Machine/base_rush_v1.py:62-111
-        uint2 st = agent_state[env * 2 + p];
-        const bool started = st.x & 1u;
-        uint32_t gnum = started ? (st.x >> 4) & 15u : 1u, nnum = started ? (st.x >> 8) & 255u : 2u;
-#pragma unroll
-        for (int k = 0; k < EVG_MAX_ACTIONS; ++k) {
-            rows[k] = 0;
-            if (started) {  // the first call only blows the turn (:73-76)
-                const uint32_t loc = rec[2 * (p * EVG_NUM_GROUPS + k)] & W0_LOC_MASK;  // GROUP k's location (:86-88)
-                const uint32_t own = p ? (uint32_t)T.p1_map[loc] : loc;
-                if (own != T.base_own[p]) {
-                    rows[k] = gnum | nnum << 8;
-                    gnum = gnum + 1 == EVG_NUM_GROUPS ? 0u : gnum + 1;
-                    if (gnum == 0) nnum = nnum % (uint32_t)T.n_nodes + 1u;
-                }
-            }
-        }
-        st.x = 1u | gnum << 4 | nnum << 8;
-        agent_state[env * 2 + p] = st;
     } else {
-        // SwarmAgent.get_action, agents/State_Machine/swarm_agent.py:79-102
+        auto w0_of = [&](int L) -> uint32_t { return rec[2 * L]; };
         uint2 st = agent_state[env * 2 + p];
-        uint32_t lst = st.y ? st.y : 0xBA875421u;  // ATTACK_LIST [1,2,4,5,7,8,10,11], :24
-        uint32_t w[4];
-        philox4x32_10(T.env_base + (uint32_t)env, turn, (uint32_t)p, 2u | episode << 8, T.seed_lo, T.seed_hi, w);
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {  // np.random.shuffle: i = 7..1, j uniform in [0, i]
-            const int ii = 7 - k;
-            const uint32_t h = (k & 1) ? w[k >> 1] >> 16 : w[k >> 1] & 0xFFFFu;
-            const int j = (int)((h * (uint32_t)(ii + 1)) >> 16);
-            const uint32_t d = ((lst >> (4 * ii)) ^ (lst >> (4 * j))) & 15u;
-            lst ^= d << (4 * ii) | d << (4 * j);
-        }
-        st.y = lst;
+        if (kind == EVG_AGENT_BASE_RUSH) agent_base_rush_rows(T, w0_of, st, p, rows);
+        else agent_swarm_rows(T, w0_of, st, T.env_base + (uint32_t)env, turn, episode, p, rows);
         agent_state[env * 2 + p] = st;
-#pragma unroll
-        for (int k = 0; k < EVG_MAX_ACTIONS; ++k) rows[k] = 0u | 1u << 8;  // default rows [0, 1], :81-82
-        int n = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t x = (lst >> (4 * k)) & 15u;
-            const uint32_t w0 = rec[2 * (p * EVG_NUM_GROUPS + x)];
-            if (n < EVG_MAX_ACTIONS && !(w0 & W0_MOVING)) {
-                const uint32_t loc = w0 & W0_LOC_MASK;
-                const uint32_t own = p ? (uint32_t)T.p1_map[loc] : loc;
-                const uint32_t row = x | (uint32_t)T.maxnb_own[p][own] << 8;
-#pragma unroll
-                for (int q = 0; q < EVG_MAX_ACTIONS; ++q)
-                    if (q == n) rows[q] = row;
-                ++n;
-            }
-        }
     }
 #pragma unroll
     for (int k = 0; k < EVG_MAX_ACTIONS; ++k) out[k] = (uint16_t)rows[k];

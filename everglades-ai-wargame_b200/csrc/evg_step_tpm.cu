@@ -263,11 +263,21 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
 #pragma unroll
             for (int r = 0; r < 2 * EVG_MAX_ACTIONS; ++r) rows[r] = (aw[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
             if (AGENTS && (A.agent[0] != EVG_AGENT_EXTERNAL || A.agent[1] != EVG_AGENT_EXTERNAL)) {
+                // the observation-driven agents read what obs[45 + 5g], obs[45 + 5g + 3] hold from the row itself; their
+                // per-(match, player) state lives in the bound agents array, like the reference's agent objects
+                auto w0_of = [&](int L) -> uint32_t { return R[2 * L]; };
 #pragma unroll
-                for (int pl = 0; pl < 2; ++pl)
-                    if (A.agent[pl] == EVG_AGENT_RANDOM)
-                        agent_random_rows(S.env_base + (uint32_t)env, turn, episode, pl, n_nodes, S.seed_lo, S.seed_hi,
-                                          rows + pl * EVG_MAX_ACTIONS);
+                for (int pl = 0; pl < 2; ++pl) {
+                    uint32_t* pr = rows + pl * EVG_MAX_ACTIONS;
+                    if (A.agent[pl] == EVG_AGENT_RANDOM) {
+                        agent_random_rows(S.env_base + (uint32_t)env, turn, episode, pl, n_nodes, S.seed_lo, S.seed_hi, pr);
+                    } else if (A.agent[pl] != EVG_AGENT_EXTERNAL) {
+                        uint2 st = A.agent_state[env * 2 + pl];
+                        if (A.agent[pl] == EVG_AGENT_BASE_RUSH) agent_base_rush_rows(S, w0_of, st, pl, pr);
+                        else agent_swarm_rows(S, w0_of, st, S.env_base + (uint32_t)env, turn, episode, pl, pr);
+                        A.agent_state[env * 2 + pl] = st;
+                    }
+                }
                 if (A.actions_out) {
                     uint32_t* ao = reinterpret_cast<uint32_t*>(A.actions_out) + env * 7;
 #pragma unroll

@@ -190,7 +190,8 @@ class BatchedEvergladesEnv:
     def step_agents(self, agent0=_capi.AGENT_RANDOM, agent1=_capi.AGENT_RANDOM, actions=None, want_actions=False):
         """One turn with scripted opponents fused into the step kernel (evg_step_agents).
 
-        agentN: _capi.AGENT_EXTERNAL (rows of that player are taken from `actions`) or _capi.AGENT_RANDOM.
+        agentN: _capi.AGENT_EXTERNAL (rows of that player are taken from `actions`), AGENT_RANDOM, AGENT_BASE_RUSH or
+        AGENT_SWARM (agents/State_Machine/*.py on the device).
         With both players scripted and want_actions=False the turn is a single launch that reads no action
         buffer; want_actions=True also writes the generated rows into the returned info["actions"]."""
         if not self._is_reset:
@@ -201,10 +202,10 @@ class BatchedEvergladesEnv:
         if ext:
             rows_t = self._as_actions(actions)
             aptr = C.c_void_p(rows_t.data_ptr())
-        elif (want_actions or not {int(agent0), int(agent1)} <= {_capi.AGENT_EXTERNAL, _capi.AGENT_RANDOM}
-              or self._lib.evg_step_kernel_kind(self._h) == 0):
-            # observation-driven agents, and any agent next to the warp-per-match kernel (small batches), run as
-            # their own kernel and hand their rows over in the action buffer
+        elif (want_actions or self._lib.evg_step_kernel_kind(self._h) == 0
+              or (self.num_nodes > 15 and _capi.AGENT_RANDOM in (int(agent0), int(agent1)))):
+            # next to the warp-per-match kernel (small batches), and for the random agent on maps too large for its
+            # register-only variant, the agents run as their own kernel and hand their rows over in the action buffer
             aptr = C.c_void_p(self._actions.data_ptr())
         _capi.check(self._lib.evg_step_agents(self._h, int(agent0), int(agent1), aptr, C.c_void_p(self.obs.data_ptr()),
                                               C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
@@ -214,6 +215,44 @@ class BatchedEvergladesEnv:
         if aptr is not None:
             info["actions"] = rows_t
         return self.obs, self.reward, self.done, info
+
+    def rollout(self, turns, agent0=_capi.AGENT_RANDOM, agent1=_capi.AGENT_RANDOM, graph_turns=50):
+        """`turns` self-play turns with both players scripted on the device, replayed from a CUDA graph.
+
+        Small and mid-size batches are launch-bound (a turn of 4,096 matches is ~10 us of GPU work), so the turn's
+        launches are captured once into a graph of `graph_turns` turns and replayed; what is left over runs as plain
+        launches.  Results are those of calling step_agents(agent0, agent1) `turns` times: the tensors hold the last
+        turn's outputs, episode statistics accumulate on the device.  graph_turns=0 disables the graph."""
+        if not self._is_reset:
+            raise RuntimeError("call reset() before rollout()")
+        torch = _torch()
+        agent0, agent1 = int(agent0), int(agent1)
+        if _capi.AGENT_EXTERNAL in (agent0, agent1):
+            raise ValueError("rollout() needs both players scripted (AGENT_RANDOM / AGENT_BASE_RUSH / AGENT_SWARM)")
+        left = int(turns)
+        if graph_turns and left >= graph_turns:
+            key = (agent0, agent1, int(graph_turns))
+            graphs = self.__dict__.setdefault("_graphs", {})
+            if key not in graphs:
+                cur = torch.cuda.current_stream(self.device)
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    self.step_agents(agent0, agent1)  # warm-up outside the capture (lazy module loading)
+                    left -= 1
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        for _ in range(graph_turns):
+                            self.step_agents(agent0, agent1)
+                cur.wait_stream(side)
+                graphs[key] = g  # (capturing does not run the turns)
+            g = graphs[key]
+            while left >= graph_turns:
+                g.replay()
+                left -= graph_turns
+        for _ in range(left):
+            self.step_agents(agent0, agent1)
+        return self.obs, self.reward, self.done, {"status": self.status, "scores": self.scores}
 
     # ------------------------------------------------------------------ host-buffer path (end-to-end)
     def host_buffers(self, obs_format="f32"):

@@ -19,9 +19,41 @@ def test_attributes_match_reference(evg):
     env = evg.EvergladesEnv()
     assert (env.num_turns, env.num_units, env.num_groups, env.num_nodes, env.num_actions_per_turn) == (150, 100, 12, 11, 7)
     assert env.unit_classes == ["controller", "striker", "tank"]
-    low, high = env.observation_space
-    assert low.shape == (105,) and high.shape == (105,)
+    # spaces as objects (everglades_env.py:25-28,124-143); callers read .shape and pass them on (dqn_training.py:66-67)
+    sp = env.observation_space
+    assert sp.shape == (105,) and sp.low.shape == (105,) and sp.high.shape == (105,)
+    assert sp.low[0] == 1 and sp.high[0] == 151 and sp.low[3] == -100 and sp.high[45] == 11
+    acts = env.action_space
+    assert len(acts.spaces) == 14 and [s.n for s in acts.spaces] == [12, 12] * 7
     assert evg.MAX_SCORE == 3700
+
+
+def test_reset_keeps_the_simulator_and_starts_a_new_episode(evg):
+    """A training loop calls reset() once per episode: nothing is reallocated while the game files stay the same, and
+    the combat tape is keyed on the episode, so identical actions fight differently in successive episodes (the
+    reference's global numpy stream carries on across resets too)."""
+    env = evg.EvergladesEnv(seed=5)
+    kw = dict(players={0: "a", 1: "b"}, config_dir=evg.DEFAULT_CONFIG_DIR, map_file="DemoMap.json", unit_file="UnitDefinitions.json")
+    # both armies march to the centre node 5 (its own number for both players): p0 1->2->5, p1 11->8 (its own 2)->5
+    script = [np.array([[g, 2] for g in range(7)]), np.array([[g, 5] for g in range(7)])]
+    healths = []
+    first_obs = None
+    for ep in range(3):
+        obs = env.reset(**kw)
+        if first_obs is None:
+            first_obs, sim = obs, env._env
+        assert env._env is sim and np.array_equal(obs[0], first_obs[0]) and np.array_equal(obs[1], first_obs[1])
+        for t in range(60):
+            a = script[0] if t < 12 else script[1]
+            env.step({0: a, 1: a})
+        st = env._env.get_state()[0]
+        assert st["episode"] == ep and st["turn"] == 60
+        healths.append(st["health"].copy())
+    assert healths[0].min() < 100.0, "the script must lead to combat"
+    assert not np.array_equal(healths[0], healths[1]) and not np.array_equal(healths[1], healths[2])
+    # other game files: a new simulator
+    env.reset(setup_file=None, **kw)
+    env.close()
 
 
 @pytest.mark.parametrize("game_idx", [0, 7, 15, 25, 27, 31])

@@ -345,9 +345,15 @@ def test_scripted_agents_match_reference_agent_games(evg, cfg):
             assert np.array_equal(rew.cpu().numpy()[0], g["reward"][t].astype(np.float32)) and int(done[0]) == g["done"][t]
 
 
-def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg):
+@pytest.mark.parametrize("kernel", ["default", "tpm", "tpm128"])
+def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg, monkeypatch, kernel):
     """65,536-style run in small: base_rush vs swarm with in-place auto-reset over several matches; agent state
-    persists across matches exactly like the oracle's (and the reference's agent objects)."""
+    persists across matches exactly like the oracle's (and the reference's agent objects).  On the thread-per-match
+    kernel the agents' rows are generated inside the step kernel: a whole self-play turn is ONE launch."""
+    if kernel != "default":
+        monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
+        if kernel == "tpm128":
+            monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")
     n = 512
     cfg.auto_reset = 1
     try:
@@ -358,9 +364,13 @@ def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg):
         ora.reset()
         for t in range(230):
             want = np.stack([ag.rows("base_rush", cfg, ora.states, 41, 3, 0), ag.rows("swarm", cfg, ora.states, 41, 3, 1)], axis=1)
-            if t % 2:
+            if t % 3 == 1:
                 obs, rew, done, info = env.step_agents(evg._capi.AGENT_BASE_RUSH, evg._capi.AGENT_SWARM, want_actions=True)
                 assert np.array_equal(info["actions"].cpu().numpy(), want), t
+            elif t % 3 == 2:
+                before = env.launch_count
+                obs, rew, done, info = env.step_agents(evg._capi.AGENT_BASE_RUSH, evg._capi.AGENT_SWARM)
+                assert env.launch_count - before == (1 if kernel != "default" else 2)  # fused into the step where possible
             else:
                 a = env.agent_actions(evg._capi.AGENT_BASE_RUSH, evg._capi.AGENT_SWARM)
                 assert np.array_equal(a.cpu().numpy(), want), t
@@ -370,6 +380,31 @@ def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg):
             assert np.array_equal(done.cpu().numpy(), odone), t
         assert env.episode_stats()["episodes"] >= 2 * n
         assert_states_equal(env.get_state(), ora.states, "end")
+    finally:
+        cfg.auto_reset = 0
+
+
+@pytest.mark.parametrize("n", [600, 16384 + 5])
+def test_rollout_from_a_cuda_graph_equals_plain_turns(evg, cfg, n):
+    """BatchedEvergladesEnv.rollout replays the self-play turn from a CUDA graph (50 turns per replay + a remainder of
+    plain launches): same final state, outputs and statistics as step_agents called turn by turn — on the warp-per-match
+    kernel (agent kernel + step) and on the thread-per-match kernel (agents fused into the step)."""
+    A = evg._capi
+    cfg.auto_reset = 1
+    try:
+        for a0, a1 in ((A.AGENT_RANDOM, A.AGENT_RANDOM), (A.AGENT_BASE_RUSH, A.AGENT_SWARM)):
+            g = evg.BatchedEvergladesEnv(n, seed=13, config=cfg, auto_reset=1, env_id_offset=2)
+            p = evg.BatchedEvergladesEnv(n, seed=13, config=cfg, auto_reset=1, env_id_offset=2)
+            g.reset()
+            p.reset()
+            g.rollout(170, a0, a1, graph_turns=50)   # 1 warm-up turn + 3 replays + 19 plain
+            for _ in range(170):
+                p.step_agents(a0, a1)
+            assert bool((g.obs == p.obs).all()) and bool((g.reward == p.reward).all()) and bool((g.done == p.done).all())
+            assert_states_equal(g.get_state(), p.get_state(), "after the rollout")
+            sg, sp = g.episode_stats(), p.episode_stats()
+            sg.pop("env_turns"), sp.pop("env_turns")   # (the host-side turn counter does not see graph replays)
+            assert sg == sp and sg["episodes"] >= n
     finally:
         cfg.auto_reset = 0
 

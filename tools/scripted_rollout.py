@@ -1,6 +1,11 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[2]: base_rushV1 (player 0) vs SwarmAgent (player 1), 65,536 lock-step matches with in-place
-auto-reset on one GPU.  Both agents run on the device (evg_agents), reading the resident records; prints one JSON line."""
+"""BASELINE.json configs[1] and configs[2] on one GPU: fully scripted self-play with in-place auto-reset, every agent
+on the device and (thread-per-match kernel) generated inside the step kernel, turns replayed from a CUDA graph
+(BatchedEvergladesEnv.rollout).
+
+    python tools/scripted_rollout.py [matches] [turns] [agent0 agent1]     agents: random | base_rush | swarm
+defaults: 65536 matches, 450 turns, base_rush vs swarm (configs[2]); `4096 900 random random` is configs[1].
+Prints one JSON line per mode: graph replay and plain launches."""
 import json
 import os
 import sys
@@ -11,25 +16,24 @@ import evgsim
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 turns = int(sys.argv[2]) if len(sys.argv) > 2 else 450
-env = evgsim.BatchedEvergladesEnv(n, seed=0, auto_reset=evgsim._capi.AUTORESET_TERMINAL)
-env.reset()
-
-
-def turn():
-    env.step(env.agent_actions(evgsim._capi.AGENT_BASE_RUSH, evgsim._capi.AGENT_SWARM))
-
-
-for _ in range(150):
-    turn()
-torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-for _ in range(turns):
-    turn()
-b.record()
-torch.cuda.synchronize()
-sec = a.elapsed_time(b) / 1e3
-st = env.episode_stats()
-print(json.dumps({"workload": "base_rushV1 vs SwarmAgent, auto-reset (BASELINE.json configs[2])", "matches": n, "turns": turns,
-                  "env_turns_per_s": n * turns / sec, "us_per_turn": sec * 1e6 / turns, "episodes": st["episodes"], "wins": st["wins"],
-                  "ties": st["ties"], "mean_episode_turns": st["total_turns"] / max(st["episodes"], 1), "status_count": st["status_count"]}))
+names = {"random": evgsim._capi.AGENT_RANDOM, "base_rush": evgsim._capi.AGENT_BASE_RUSH, "swarm": evgsim._capi.AGENT_SWARM}
+a0 = names[sys.argv[3]] if len(sys.argv) > 4 else names["base_rush"]
+a1 = names[sys.argv[4]] if len(sys.argv) > 4 else names["swarm"]
+label = "%s vs %s" % tuple(k for v in (a0, a1) for k, vv in names.items() if vv == v)
+for graph_turns in (50, 0):
+    env = evgsim.BatchedEvergladesEnv(n, seed=0, auto_reset=evgsim._capi.AUTORESET_TERMINAL)
+    env.reset()
+    env.rollout(150, a0, a1, graph_turns=graph_turns)  # warm-up episode (captures the graph)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    env.rollout(turns, a0, a1, graph_turns=graph_turns)
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / 1e3
+    st = env.episode_stats()
+    print(json.dumps({"workload": "%s, auto-reset" % label, "matches": n, "turns": turns, "mode": "cuda graph of 50 turns" if graph_turns else "plain launches",
+                      "step_kernel_kind": env._lib.evg_step_kernel_kind(env._h), "env_turns_per_s": n * turns / sec, "us_per_turn": sec * 1e6 / turns,
+                      "episodes": st["episodes"], "wins": st["wins"], "ties": st["ties"],
+                      "mean_episode_turns": st["total_turns"] / max(st["episodes"], 1), "status_count": st["status_count"]}), flush=True)
+    env.close()
