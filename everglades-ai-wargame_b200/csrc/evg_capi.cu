@@ -352,7 +352,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.action_bytes = 2 * EVG_MAX_ACTIONS * 2;
     L.records_bytes = n_envs * L.record_bytes;
     L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
-    L.stats_bytes = evg::ST_COUNT * 8;
+    L.stats_bytes = (evg::ST_COUNT + evg::kSchedSlots) * 8;  // + the step kernel's batch hand-out counters
     L.agents_bytes = n_envs * 16;
     // loss table, then reciprocals, then the Tables struct itself (the step kernel stages it from here)
     L.tables_bytes = round_up((int)((int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8), 16) + round_up((int)sizeof(evg::Tables), 16);
@@ -462,7 +462,7 @@ int evg_reset_fmt(EvgSim* sim, int32_t format, const uint8_t* d_mask, void* d_ro
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (!d_mask) {
-        if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_STATS], 0, evg::ST_COUNT * 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(stats)");
+        if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_STATS], 0, (size_t)sim->layout.stats_bytes, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(stats)");
         if ((e = cudaMemsetAsync(sim->bound[EVG_BIND_AGENTS], 0, (size_t)sim->n_envs * 16, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agent state)");
         sim->steps = 0;
     }
@@ -484,7 +484,7 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) { 
 // chunks; all the per-match arrays are offset here, the kernel adds `first` to the global match ids)
 static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_actions, int8_t* d_actions_out, void* d_obs,
                      float* d_reward, uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream, int64_t first = 0,
-                     int64_t count = -1, int obs_fmt = EVG_OBS_F32)
+                     int64_t count = -1, int obs_fmt = EVG_OBS_F32, int sched_slot = 0)
 {
     evg::StepArgs a;
     a.agent[0] = agent0;
@@ -494,6 +494,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.health = (double*)sim->bound[EVG_BIND_HEALTH];
     a.stats = (unsigned long long*)sim->bound[EVG_BIND_STATS];
     a.agent_state = (uint2*)sim->bound[EVG_BIND_AGENTS];
+    a.sched = (unsigned*)((unsigned long long*)sim->bound[EVG_BIND_STATS] + evg::ST_COUNT + sched_slot);
     a.actions = d_actions;
     a.obs = (float*)d_obs;
     a.obs_fmt = obs_fmt;
@@ -594,11 +595,11 @@ int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void
     const char* what = "";
 #define EVG_TRY(call, name) do { if (e == cudaSuccess && (e = (call)) != cudaSuccess) what = name; } while (0)
     // one sub-range [first, first + cnt): H2D of its action rows, the step, (the narrowing,) D2H of its results, all on `cs`
-    auto chunk = [&](cudaStream_t cs, int64_t first, int64_t cnt, bool sub) -> int {
+    auto chunk = [&](cudaStream_t cs, int64_t first, int64_t cnt, bool sub, int slot) -> int {
         EVG_TRY(cudaMemcpyAsync(d_actions + first * ab, h_actions + first * ab, (size_t)cnt * ab, cudaMemcpyHostToDevice, cs), "H2D actions");
         if (e != cudaSuccess) return EVG_OK;
         int r = step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, i16 ? (void*)d_obs_f32 : d_rows, d_reward, d_done, nullptr,
-                          nullptr, cs, sub ? first : 0, sub ? cnt : -1, wire ? EVG_OBS_WIRE : EVG_OBS_F32);
+                          nullptr, cs, sub ? first : 0, sub ? cnt : -1, wire ? EVG_OBS_WIRE : EVG_OBS_F32, slot);
         if (r) return r;
         if (i16) {
             EVG_TRY(evg::launch_obs_to_i16((const float*)((const char*)d_obs_f32 + first * fb), (int16_t*)((char*)d_rows + first * rb),
@@ -641,7 +642,7 @@ int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void
         for (int i = 0; i < 2; ++i) EVG_TRY(cudaStreamWaitEvent(sim->host_stream[i], sim->host_start, 0), "cudaStreamWaitEvent");
         int c = 0;
         for (int64_t first = 0; first < n && e == cudaSuccess && rc == EVG_OK; first += per, ++c)
-            rc = chunk(sim->host_stream[c & 1], first, n - first < per ? n - first : per, true);
+            rc = chunk(sim->host_stream[c & 1], first, n - first < per ? n - first : per, true, c & 1);  // a counter pair per stream
         // join: `stream` waits for both library streams whatever happened above
         for (int i = 0; i < 2; ++i) {
             cudaError_t j = cudaEventRecord(sim->host_done[i], sim->host_stream[i]);
@@ -652,7 +653,7 @@ int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void
             }
         }
     } else {
-        rc = chunk(st, 0, n, false);
+        rc = chunk(st, 0, n, false, 0);
     }
 #undef EVG_TRY
     if (rc) return rc;

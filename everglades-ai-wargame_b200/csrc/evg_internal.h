@@ -45,7 +45,8 @@ struct alignas(16) Tables {
     float max_score_f;
     float pad5;
     // per-warp shared-memory carve-up (bytes)
-    int32_t sm_acc, sm_hist, sm_obs, sm_misc, sm_warp_stride, sm_tables_bytes, pad3, pad4;
+    int32_t sm_acc, sm_hist, sm_obs, sm_misc, sm_warp_stride, sm_tables_bytes;
+    uint32_t cta_sched[2];  // 0 here; in a CTA's shared-memory copy: the batch indices thread 0 drew for the CTA (thread-per-match kernel)
     double node_def[kNN];
     double unit_armor[EVG_MAX_UNIT_TYPES];
     uint32_t init_w0[kGroupLanes], init_w1[kGroupLanes];
@@ -107,6 +108,7 @@ constexpr int kTpmStage = EVG_TPM_STAGE;  // observation staging window per matc
 // ST_FOUGHT: unit slots of the groups that took part in combat (every match-turn, finished or not): the health term of
 // the step's algorithmic bytes is 16 B per such slot, so bench.py can state it for the turns it timed
 enum { ST_EPISODES = 0, ST_WIN0, ST_WIN1, ST_TIES, ST_TURNS, ST_SCORE0, ST_SCORE1, ST_STATUS0, ST_FOUGHT = ST_STATUS0 + 4, ST_COUNT };
+constexpr int kSchedSlots = 2;  // behind the statistics in the same bound array: one counter pair (8 bytes) per concurrent launch
 
 struct StepArgs {
     uint32_t* records;
@@ -124,6 +126,7 @@ struct StepArgs {
     const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
     int64_t env_first;        // thread-per-match kernel: this launch covers matches [env_first, env_first + n_envs) of the
                               // simulator (all pointers above are already offset); 0 for a whole-batch launch
+    unsigned* sched;          // thread-per-match kernel: {batches handed out after the first wave, CTAs finished}, zero between launches
     uint2* agent_state;       // per (match, player) state of the observation-driven scripted agents (bind slot EVG_BIND_AGENTS)
     int32_t obs_fmt;          // EVG_OBS_F32: `obs` is float32[n][2][obs_len]; EVG_OBS_WIRE: packed rows of wire_bytes(n_nodes)
 };

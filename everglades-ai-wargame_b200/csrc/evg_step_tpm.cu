@@ -64,16 +64,15 @@ namespace {
 
 constexpr int kMoveUnroll = EVG_TPM_MOVE_UNROLL, kCaptureUnroll = EVG_TPM_CAPTURE_UNROLL;
 
-// game_init state (server.py:133-209) for one match: record row in shared memory + health refill
-__device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* health, int n_nodes, uint32_t* X = nullptr)
+// game_init state (server.py:133-209) for one match: its record row in shared memory (the health refill is the warp's
+// job: refill_health below)
+__device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, int n_nodes, uint32_t* X = nullptr)
 {
     for (int L = 0; L < kGroupLanes; ++L) {
         R[2 * L] = S.init_w0[L];
         R[2 * L + 1] = S.init_w1[L];
     }
     for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
-    double2* hp = reinterpret_cast<double2*>(health);
-    for (int i = 0; i < S.health_slots / 2; ++i) hp[i] = make_double2(100.0, 100.0);  // definitions.py:62
     if (X) {  // EVG_AUTORESET_NEXT: the observation shows the new match, so its node sums are needed too
         const int nn = n_nodes + 1;
         for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
@@ -81,6 +80,16 @@ __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, double* hea
             const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
             X[32 * ((L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK))] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;
         }
+    }
+}
+
+// health 100.0 for every unit of the matches in `mask` (definitions.py:62), written by the whole warp match after match
+// with coalesced 16-byte stores: one finished match costs 4 store instructions, not 100 by a single lane
+__device__ __noinline__ void refill_health(double* health_warp, int slots, uint32_t mask, int lane)
+{
+    for (; mask; mask &= mask - 1) {
+        double2* hp = reinterpret_cast<double2*>(health_warp + (size_t)(__ffs(mask) - 1) * slots);
+        for (int i = lane; i < slots / 2; i += 32) hp[i] = make_double2(100.0, 100.0);
     }
 }
 
@@ -164,6 +173,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         return true;
     };
     if (PIPE) have = request(blockIdx.x);  // the first batch's records travel while the tables are staged
+    // Batches are handed out DYNAMICALLY after the first wave (a CTA's first batch is its block index): matches in
+    // different phases of the game cost different amounts (no fight / fights / in-place reset), and a static round-robin
+    // leaves the SMs with the cheap batches idle at the end.  Thread 0 draws the batch after next from a global counter
+    // ahead of the one CTA barrier of a batch and publishes it in shared memory; the counter pair (handed out, CTAs
+    // finished) resets itself when the last CTA leaves.
+    static_assert(EVG_TPM_SYNC && ((EVG_TPM_SYNC_MASK >> 3) & 1), "the batch hand-over uses the barrier before the observation phase");
+    // (the two hand-over slots live in the CTA's copy of the tables: static shared memory would come off the opt-in limit)
+    uint32_t first_draw = 0;
+    if (threadIdx.x == 0) first_draw = gridDim.x + atomicAdd(&A.sched[0], 1u);
     // ---- stage the static tables once per CTA
     {   // from device memory with coalesced 16-byte loads (per-lane addresses into the parameter bank would be serialised)
         static_assert(sizeof(Tables) % 16 == 0, "Tables is copied in 16-byte pieces");
@@ -172,10 +190,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     }
     const Tables& S = *reinterpret_cast<const Tables*>(smem);
     __syncthreads();
-    if (A.env_first) {  // a sub-range launch (evg_step_host's chunks): global match ids start further on
-        if (threadIdx.x == 0) reinterpret_cast<Tables*>(smem)->env_base += (uint32_t)A.env_first;
-        __syncthreads();
+    volatile uint32_t* sched = reinterpret_cast<Tables*>(smem)->cta_sched;
+    if (threadIdx.x == 0) {
+        sched[0] = first_draw;
+        // a sub-range launch (evg_step_host's chunks): global match ids start further on
+        reinterpret_cast<Tables*>(smem)->env_base += (uint32_t)A.env_first;
     }
+    int par = 1;
 
     const Geo<NODES> G(S);
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
@@ -207,6 +228,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         oconst[f] = v;
     }
     __syncthreads();
+    int64_t next_batch = sched[0];
     const int P = PITCH ? PITCH : T.tpm_pitch;
     const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
     // per warp: 32 rows (record + observation staging window), the node words of its 32 matches stored
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     uint32_t* pool = wx + 64 * nn;          // the warp's histogram pool
     // persistent CTA: batches of 128 consecutive matches, round-robin over the grid; a warp only ever
     // touches its own 32 rows, so batches need no CTA-wide barrier
-    for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+    for (int64_t batch = blockIdx.x; batch < nbatches;) {
     const int64_t warp_env0 = batch * THREADS + warp * 32;
     const int64_t env = warp_env0 + lane;
     const int64_t left = A.n_envs - warp_env0;
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         // (action rows requested before the records so the latencies overlap)
 #pragma unroll
         for (int k = 0; k < 7; ++k) aw[k] = (valid && ext_rows) ? __ldcs(reinterpret_cast<const uint32_t*>(A.actions) + env * 7 + k) : 0u;
-        load_rows_direct<NODES>(A, wrow, P, RW, RWU, warp_env0, nvalid, lane, !PIPE, warp_env0 + (int64_t)gridDim.x * THREADS);
+        load_rows_direct<NODES>(A, wrow, P, RW, RWU, warp_env0, nvalid, lane, !PIPE, next_batch * THREADS + warp * 32);
     }
     __syncwarp();
     EVG_PHASE_SYNC(0);
@@ -509,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
 
     EVG_PHASE_SYNC(2);
 #if EVG_TPM_REQUEST_AT == 1
-    if (PIPE) have = request(batch + gridDim.x);
+    if (PIPE) have = request(next_batch);
 #endif
     if (valid) {
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
@@ -611,17 +633,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     }
     const bool reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
     // ---- episode end: statistics, aggregated over the warp before touching the global counters
-    if (__any_sync(0xFFFFFFFFu, reset_now)) episode_stats(A.stats, reset_now, s0, s1, turn, status, lane);
+    if (const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, reset_now)) {
+        episode_stats(A.stats, reset_now, s0, s1, turn, status, lane);
+        refill_health(A.health + warp_env0 * S.health_slots, S.health_slots, rmask, lane);
+    }
     if (reset_now && S.auto_reset == EVG_AUTORESET_NEXT) {
-        reset_row(S, R, A.health + env * S.health_slots, n_nodes, X);
+        reset_row(S, R, n_nodes, X);
         turn = 0;
         episode += 1;
     }
 
 #if EVG_TPM_REQUEST_AT == 0
-    if (PIPE) have = request(batch + gridDim.x);  // in flight across the barrier
+    if (PIPE) have = request(next_batch);  // in flight across the barrier
 #endif
+    if (threadIdx.x == 0) sched[par] = gridDim.x + atomicAdd(&A.sched[0], 1u);  // the batch after next
     EVG_PHASE_SYNC(3);
+    const int64_t after_next = sched[par];
+    par ^= 1;
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
     // Each thread packs kTpmStage words at a time into the staging window of its row; the warp streams the
@@ -717,7 +745,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         }
     }
     if (reset_now && S.auto_reset == EVG_AUTORESET_TERMINAL) {
-        reset_row(S, R, A.health + env * S.health_slots, n_nodes);
+        reset_row(S, R, n_nodes);
         turn = 0;
         episode += 1;
     }
@@ -754,9 +782,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         }
     }
     __syncwarp();
+    batch = next_batch;
+    next_batch = after_next;
     }  // batch loop
     __syncthreads();
-    if (threadIdx.x == 0 && S.cta_fought) atomicAdd(&A.stats[ST_FOUGHT], (unsigned long long)S.cta_fought);
+    if (threadIdx.x == 0) {
+        if (S.cta_fought) atomicAdd(&A.stats[ST_FOUGHT], (unsigned long long)S.cta_fought);
+        __threadfence();
+        if (atomicAdd(&A.sched[1], 1u) == gridDim.x - 1) {  // the last CTA out: every hand-out has happened
+            A.sched[0] = 0u;
+            A.sched[1] = 0u;
+        }
+    }
 }
 
 // DemoMap row: 62 record words + the staging window, pitch / 2 odd

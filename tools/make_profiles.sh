@@ -7,7 +7,7 @@ set -e
 tag=$1; rep=$(realpath $2); lib=$(realpath $3); launches=${4:+$(realpath $4)}
 here=$(dirname $(realpath $0)); root=$(dirname $here); out=$root/profiles
 src=$root/everglades-ai-wargame_b200/csrc/evg_step_tpm.cu
-k=${KERNEL:-evg_step_tpm_kernelILi11ELi12EhLi94ELb0ELi128}
+k=${KERNEL:-evg_step_tpm_kernelILi11ELi12EhLi94ELb0ELi128ELb0E}
 matches=${MATCHES:-262144}
 d=$(mktemp -d); cd $d
 ncu -i $rep --page source --csv > sass.csv 2>/dev/null

@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/ncu_report.sh REPORT.ncu-rep LIB.so SOURCE.cu [kernel-substring]  ->  phase table, stall mix, hottest lines
 set -e
-rep=$(realpath $1); lib=$(realpath $2); src=$(realpath $3); k=${4:-evg_step_tpm_kernelILi11ELi12EhLi94ELb0ELi128}
+rep=$(realpath $1); lib=$(realpath $2); src=$(realpath $3); k=${4:-evg_step_tpm_kernelILi11ELi12EhLi94ELb0ELi128ELb0E}
 here=$(dirname $(realpath $0))
 d=$(mktemp -d); cd $d
 ncu -i $rep --page source --csv > sass.csv 2>/dev/null
