@@ -152,6 +152,7 @@ SYMBOLS = [
     ("evg_reset", C.c_int, [_P, _P, _P, _P]),
     ("evg_step", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_step_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    ("evg_rollout", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_step_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("evg_obs_row_bytes", C.c_int, [_P, C.c_int32]),
     ("evg_reset_fmt", C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),

@@ -563,6 +563,48 @@ int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_a
     return step_impl(sim, EVG_AGENT_EXTERNAL, EVG_AGENT_EXTERNAL, d_actions, nullptr, d_obs, d_reward, d_done, d_status, d_scores, stream);
 }
 
+int evg_rollout(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int32_t n_turns, int8_t* d_actions, float* d_obs, float* d_reward,
+                uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream)
+{
+    int rc = check_sim(sim, true);
+    if (rc) return rc;
+    if (!d_actions || !d_obs || !d_reward || !d_done) return fail(EVG_E_ARG, "evg_rollout: actions/obs/reward/done must be non-null");
+    if (n_turns < 0) return fail(EVG_E_ARG, "evg_rollout: n_turns %d is negative", n_turns);
+    const int ag[2] = {agent_p0, agent_p1};
+    for (int p = 0; p < 2; ++p)
+        if (ag[p] <= EVG_AGENT_EXTERNAL || ag[p] > EVG_AGENT_SWARM) return fail(EVG_E_ARG, "evg_rollout: player %d needs a scripted agent, got %d", p, ag[p]);
+    const bool random_big_map = (agent_p0 == EVG_AGENT_RANDOM || agent_p1 == EVG_AGENT_RANDOM) && sim->cfg.n_nodes > evg::kAgentMaxNodes;
+    if (sim->use_tpm || random_big_map) {  // one launch (or agent kernel + step) per turn; a caller may capture this in a CUDA graph
+        for (int k = 0; k < n_turns; ++k)
+            if ((rc = evg_step_agents(sim, agent_p0, agent_p1, d_actions, d_obs, d_reward, d_done, d_status, d_scores, stream))) return rc;
+        return EVG_OK;
+    }
+    if (n_turns == 0) return EVG_OK;
+    evg::StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.agent[0] = agent_p0;
+    a.agent[1] = agent_p1;
+    a.actions = d_actions;
+    a.actions_out = d_actions;
+    a.records = (uint32_t*)sim->bound[EVG_BIND_RECORDS];
+    a.health = (double*)sim->bound[EVG_BIND_HEALTH];
+    a.stats = (unsigned long long*)sim->bound[EVG_BIND_STATS];
+    a.agent_state = (uint2*)sim->bound[EVG_BIND_AGENTS];
+    a.obs = d_obs;
+    a.obs_fmt = EVG_OBS_F32;
+    a.reward = d_reward;
+    a.done = d_done;
+    a.status = d_status;
+    a.scores = d_scores;
+    a.n_envs = sim->n_envs;
+    a.tables_dev = sim->tables_dev;
+    cudaError_t e = evg::launch_rollout(sim->tables, a, n_turns, sim->grid, sim->smem, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_rollout_kernel launch");
+    sim->launches += 1;
+    sim->steps += n_turns;
+    return EVG_OK;
+}
+
 int evg_step_fmt(EvgSim* sim, int32_t format, const int8_t* d_actions, void* d_rows, float* d_obs_f32, float* d_reward,
                  uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream)
 {

@@ -147,6 +147,7 @@ inline cudaError_t optin_smem_limit(size_t needed, int* limit)
 
 // launchers (evg_kernels.cu); all asynchronous on `stream`, return the launch error
 cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_rollout(const Tables& t, const StepArgs& a, int n_turns, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, void* obs, int obs_fmt,
                          int64_t n_envs, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_obs_to_i16(const float* obs, int16_t* out, int64_t n_values, cudaStream_t stream);
@@ -170,6 +171,17 @@ cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blo
 cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, size_t smem, int max_grid, cudaStream_t stream);
 
 #ifdef __CUDACC__
+// -DEVG_CHECKED (tools/build_variant.sh checked -DEVG_CHECKED): every data-dependent shared-memory index, health offset
+// and match index of the step kernels is asserted in range — the project's own substitute for compute-sanitizer's
+// memcheck on pools where the sanitizer is not available.  The GPU test-suite is run against that build
+// (EVGSIM_LIB=build/libevgsim_checked.so; profiles/README.md).  Compiles to nothing in the product build.
+#ifdef EVG_CHECKED
+#include <cassert>
+#define EVG_CHECK(cond) assert(cond)
+#else
+#define EVG_CHECK(cond) ((void)0)
+#endif
+
 // Philox4x32-10 (Salmon et al., SC'11); same function as oracle/tape.py, oracle/evg_oracle.c.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                                uint32_t out[4])

@@ -169,7 +169,8 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
     uint2 own = make_uint2(0u, 0u);
     if (lane < rec_words8) own = grec[lane];
     uint32_t arow = 0;
-    if (lane < 2 * EVG_MAX_ACTIONS) arow = reinterpret_cast<const uint16_t*>(A.actions)[env * (2 * EVG_MAX_ACTIONS) + lane];
+    // (L1-bypassing load: in the multi-turn rollout kernel the rows were written a moment ago by two lanes of this warp)
+    if (lane < 2 * EVG_MAX_ACTIONS) arow = __ldcg(reinterpret_cast<const uint16_t*>(A.actions) + env * (2 * EVG_MAX_ACTIONS) + lane);
     if (lane < rec_words8) srec2[lane] = own;
     for (int i = lane + 32; i < rec_words8; i += 32) srec2[i] = grec[i];
     if (is_grp) W.cmd[lane] = 0xFFFFFFFFu;
@@ -192,6 +193,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
             if (pl) an = S.p1_map[an];  // server.py:233-234
             const int L = pl * EVG_NUM_GROUPS + ag;
             const uint32_t gw0 = W.rec[2 * L];
+            EVG_CHECK((gw0 & W0_LOC_MASK) >= 1 && (gw0 & W0_LOC_MASK) <= (uint32_t)n_nodes && an >= 0 && an <= n_nodes);
             const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
             if (d && !(gw0 & W0_MOVING)) atomicMin(&W.cmd[L], (uint32_t)lane << 16 | (uint32_t)an << 8 | d);
         }
@@ -228,6 +230,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
             //   acc[nn + x] = exclusive prefix of acc over nodes = histogram base of (side, x)
             for (int i = lane; i < nn; i += 32) W.acc[i] = 0;
             __syncwarp();
+            EVG_CHECK(!fighting || (loc >= 1 && loc <= (uint32_t)n_nodes));
             if (fighting) atomicAdd(&W.acc[loc], cnt << (16 * side));
             __syncwarp();
             const uint32_t tot = lane < n_nodes ? W.acc[lane + 1] : 0u;
@@ -241,6 +244,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
             const uint32_t totals = __shfl_sync(FULL, inc, 31);
             if (lane < n_nodes) W.acc[nn + lane + 1] = inc - tot;
             const int hw0 = (int)((totals & 0xFFFFu) + 1) >> 1, hw1 = (int)((totals >> 16) + 1) >> 1;
+            EVG_CHECK(hw0 <= S.hist_words && hw1 <= S.hist_words);
             for (int i = lane; i < hw0; i += 32) W.hist[i] = 0;
             for (int i = lane; i < hw1; i += 32) W.hist[S.hist_words + i] = 0;
             __syncwarp();
@@ -266,6 +270,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
             const uint32_t b2 = __ballot_sync(FULL, fighting && cnt > 8);
             const uint32_t lt = (1u << lane) - 1u;
             const int o1 = __popc(fmask), npairs = o1 + __popc(b2), nsegs = o1 + __popc(big);
+            EVG_CHECK(npairs <= 96 && nsegs <= 48);
             if (fighting) {
                 W.pair[__popc(fmask & lt)] = (uint8_t)lane;
                 W.seg[__popc(fmask & lt)] = (uint8_t)lane;
@@ -296,6 +301,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                         if (8 * k + q < gcnt) {
                             const uint32_t half = (q & 1) ? r[q >> 1] >> 16 : r[q >> 1] & 0xFFFFu;
                             const uint32_t idx = ghb + ((half * gn) >> 16);
+                            EVG_CHECK(gn >= 1 && (int)(idx >> 1) < S.hist_words);
                             atomicAdd(&hist[idx >> 1], dmg << ((idx & 1u) * 16));
                         }
                 }
@@ -319,6 +325,7 @@ __device__ __forceinline__ void step_match(const Tables& S, const WarpSmem& W, c
                 uint32_t d = 0;
                 if (mine) {
                     const uint32_t idx = (W.cmd[L] & 0xFFu) + __popc(galive & ((1u << slot) - 1u));
+                    EVG_CHECK((int)(idx >> 1) < S.hist_words && (int)S.g_slot[L] + slot < S.health_slots);
                     d = (W.hist[gs * S.hist_words + (idx >> 1)] >> ((idx & 1u) * 16)) & 0xFFFFu;
                     h = *hp;
                 }
@@ -524,6 +531,53 @@ __global__ void __launch_bounds__(kThreads, 4) evg_step_kernel(const __grid_cons
     const WarpSmem W = carve(smem + T.sm_tables_bytes + 128 + warp * T.sm_warp_stride, S);
     for (int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + warp; env < A.n_envs; env += (int64_t)gridDim.x * kWarpsPerBlock)
         step_match<NODES>(S, W, A, env, lane, cta_stats);
+    __syncthreads();
+    if (threadIdx.x < ST_COUNT && cta_stats[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], cta_stats[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-turn rollout for small batches: fully scripted self-play (both players' rows from the on-device agents),
+// `n_turns` game turns per launch.  A warp keeps its match for all the turns — the record and the health rows it
+// re-reads every turn are its own last writes, still in L1/L2 — so a turn costs no launch and no action-buffer pass:
+// lanes 0 and 1 generate the two players' rows (agents/State_Machine/*.py, same functions as evg_agents_kernel) into
+// the match's slot of the action buffer, the warp steps the match (step_match, unchanged), repeat.  The output
+// arrays hold the last turn's observations / rewards / done flags; episode statistics accumulate as usual.
+// ---------------------------------------------------------------------------------------------
+template <int NODES>
+__global__ void __launch_bounds__(kThreads, 4) evg_rollout_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A, int n_turns)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables& S = stage_tables(T, smem);
+    unsigned long long* cta_stats = reinterpret_cast<unsigned long long*>(smem + T.sm_tables_bytes);
+    if (threadIdx.x < ST_COUNT) cta_stats[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WarpSmem W = carve(smem + T.sm_tables_bytes + 128 + warp * T.sm_warp_stride, S);
+    const int rec_words = S.rec_words8 * 2;
+    for (int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + warp; env < A.n_envs; env += (int64_t)gridDim.x * kWarpsPerBlock) {
+        const uint32_t* rec = A.records + env * rec_words;
+        for (int k = 0; k < n_turns; ++k) {
+            if (lane < 2) {
+                const int p = lane, kind = A.agent[p];
+                const uint32_t turn = __ldcg(rec + kRecTurn) + 1u, episode = __ldcg(rec + kRecEpisode);
+                uint32_t rows[EVG_MAX_ACTIONS];
+                if (kind == EVG_AGENT_RANDOM) {
+                    agent_random_rows(S.env_base + (uint32_t)env, turn, episode, p, S.n_nodes, S.seed_lo, S.seed_hi, rows);
+                } else {
+                    auto w0_of = [&](int L) -> uint32_t { return __ldcg(rec + 2 * L); };
+                    uint2 st = A.agent_state[env * 2 + p];
+                    if (kind == EVG_AGENT_BASE_RUSH) agent_base_rush_rows(S, w0_of, st, p, rows);
+                    else agent_swarm_rows(S, w0_of, st, S.env_base + (uint32_t)env, turn, episode, p, rows);
+                    A.agent_state[env * 2 + p] = st;
+                }
+                uint16_t* out = reinterpret_cast<uint16_t*>(A.actions_out + (env * 2 + p) * (EVG_MAX_ACTIONS * 2));
+#pragma unroll
+                for (int r = 0; r < EVG_MAX_ACTIONS; ++r) out[r] = (uint16_t)rows[r];
+            }
+            __syncwarp();
+            step_match<NODES>(S, W, A, env, lane, cta_stats);
+        }
+    }
     __syncthreads();
     if (threadIdx.x < ST_COUNT && cta_stats[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], cta_stats[threadIdx.x]);
 }
@@ -824,11 +878,20 @@ __global__ void evg_shape_reward_kernel(int mode, const float* reward, const uin
 // DemoMap's node count gets a compile-time instantiation; any other map runs the generic one.
 constexpr int kFastNodes = 11;
 
+cudaError_t launch_rollout(const Tables& t, const StepArgs& a, int n_turns, int grid, size_t smem, cudaStream_t stream)
+{
+    if (t.n_nodes == kFastNodes) evg_rollout_kernel<kFastNodes><<<grid, kThreads, smem, stream>>>(t, a, n_turns);
+    else evg_rollout_kernel<0><<<grid, kThreads, smem, stream>>>(t, a, n_turns);
+    return cudaGetLastError();
+}
+
 cudaError_t set_step_smem(size_t smem)
 {
     int limit = 0;
     cudaError_t e = optin_smem_limit(smem, &limit);
     if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_rollout_kernel<kFastNodes>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(evg_rollout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(evg_step_kernel<kFastNodes>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(evg_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;

@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 if (pl) an = (int)p1map((uint32_t)an);  // server.py:233-234
                 const int L = pl * EVG_NUM_GROUPS + (okg ? ag : 0);
                 const uint32_t gw0 = R[2 * L];
+                EVG_CHECK(L >= 0 && L < kGroupLanes && (gw0 & W0_LOC_MASK) >= 1 && (gw0 & W0_LOC_MASK) <= (uint32_t)n_nodes && an >= 0 && an <= n_nodes);
                 const uint32_t d = S.edge[gw0 & W0_LOC_MASK][an];
                 Lr[r] = L;
                 if (okg && !(gw0 & W0_MOVING) && d) okrows |= 1u << r;  // t2 (not moving) and t3 (adjacent), :243-250
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                     const uint32_t aa = wa.y & 0xFFFFu, ab = wb.y & 0xFFFFu;
                     const bool pa = aa && !(wa.x & W0_MOVING), pb = ab && !(wb.x & W0_MOVING);
                     const uint32_t la = pa ? wa.x & W0_LOC_MASK : 0u, lb = pb ? wb.x & W0_LOC_MASK : 0u;
+                    EVG_CHECK(la <= (uint32_t)n_nodes && lb <= (uint32_t)n_nodes);
                     // shared-memory reductions (no value returned): one instruction per update and nothing to wait for
                     atomicAdd(&acc0[32 * la], 1u << g | (uint32_t)__popc(aa) << 16);
                     atomicAdd(&acc1[32 * lb], 1u << g | (uint32_t)__popc(ab) << 16);
@@ -437,6 +439,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 const int pc = __shfl_sync(0xFFFFFFFFu, pre, cand & 31);
                 if (cand < 32 && pc <= q) m = cand;
             }
+            EVG_CHECK(m >= 0 && m < 32 && nround >= 1 && nround <= 32 && m_end > m_begin && m_end <= 32);
+            EVG_CHECK((uround * (uint32_t)sizeof(HistT) + 3u) / 4u <= (uint32_t)T.tpm_pool_words);
             const int pm = __shfl_sync(0xFFFFFFFFu, pre, m);
             const uint32_t fmm = __shfl_sync(0xFFFFFFFFu, fm, m), xmm = __shfl_sync(0xFFFFFFFFu, xm, m);
             const uint32_t ubm = __shfl_sync(0xFFFFFFFFu, ub, m);
@@ -454,9 +458,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             __syncwarp();  // pool zeroed
             if (act) {
                 L = extra ? kth_set_bit(xmm, q - pm - nf) : kth_set_bit(fmm, q - pm);
+                EVG_CHECK(L >= 0 && L < kGroupLanes && (!act || (m >= m_begin && m < m_end)));
                 gf = S.g_fight[L];  // health slot | unit slots << 12 | damage << 17 | unit type << 25
                 if (!extra) {
                     hp = A.health + (warp_env0 + m) * S.health_slots + (gf & 0xFFFu);
+                    EVG_CHECK(warp_env0 + m < A.n_envs && (int)(gf & 0xFFFu) + ((int)((gf >> 12) & 31u) + 3) / 4 * 4 <= S.health_slots);
                     load_group<MAXSZ>(hp, (int)((gf >> 12) & 31u), hv);  // consumed after the draws
                 }
                 side = L >= EVG_NUM_GROUPS ? 1 : 0;
@@ -467,6 +473,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                     w1 = w.y;
                 }
                 x = (int)(w0 & W0_LOC_MASK);
+                EVG_CHECK(x >= 1 && x <= n_nodes);
                 const uint32_t cnt = __popc(w1 & 0xFFFFu);
                 const uint32_t own = Xm[32 * (side * nn + x)], opp = Xm[32 * ((1 - side) * nn + x)];
                 const uint32_t n = (opp >> 16) & 0xFFu;                        // opposing units at the node
@@ -500,6 +507,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                         if (8u * (b - jb) + k < nd) {
                             const uint32_t half = (k & 1) ? r[k >> 1] >> 16 : r[k >> 1] & 0xFFFFu;
                             const uint32_t idx = hb + ((half * n) >> 16);
+                            EVG_CHECK(n >= 1 && idx < uround);
                             if (sizeof(HistT) == 1) atomicAdd(&pool[idx >> 2], dmg << ((idx & 3u) * 8));
                             else atomicAdd(&pool[idx >> 1], dmg << ((idx & 1u) * 16));
                         }
@@ -517,6 +525,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 constexpr bool FMA_ONLY = NODES != 0;  // the compile-time map's kernel is only picked when Tables::fast_div holds
                 const double* ltab = FMA_ONLY || S.fast_div ? nullptr : S.loss_tab + (size_t)ti * kLossD;
                 const double rcp = FMA_ONLY || S.fast_div ? __ldg(S.rcp_tab + ti) : 0.0;
+                EVG_CHECK(tb >= 0 && (uint32_t)tb + (uint32_t)__popc(w1 & 0xFFFFu) <= uround && ti >= 0);
                 int avg;
                 const uint32_t alive = apply_group<MAXSZ, HistT, FMA_ONLY>(hp, hv, (int)((gf >> 12) & 31u), w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
                                                                            tb, ltab, divisor, &avg, rcp);
@@ -572,6 +581,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 const uint2 gm = *reinterpret_cast<const uint2*>(&S.g_move[2 * g]);  // {player 0's, player 1's}: speed | control << 8 | cost << 16
                 move(g, gm.x, va, la, pa);
                 move(EVG_NUM_GROUPS + g, gm.y, vb, lb, pb);
+                EVG_CHECK(la <= (uint32_t)n_nodes && lb <= (uint32_t)n_nodes);
                 atomicAdd(&acc0[32 * la], va);  // entry 0 collects the (zero) contributions of dead groups
                 atomicAdd(&acc1[32 * lb], vb);
                 s0 += pa;

@@ -217,11 +217,11 @@ class BatchedEvergladesEnv:
         return self.obs, self.reward, self.done, info
 
     def rollout(self, turns, agent0=_capi.AGENT_RANDOM, agent1=_capi.AGENT_RANDOM, graph_turns=50):
-        """`turns` self-play turns with both players scripted on the device, replayed from a CUDA graph.
+        """`turns` self-play turns with both players scripted on the device.
 
-        Small and mid-size batches are launch-bound (a turn of 4,096 matches is ~10 us of GPU work), so the turn's
-        launches are captured once into a graph of `graph_turns` turns and replayed; what is left over runs as plain
-        launches.  Results are those of calling step_agents(agent0, agent1) `turns` times: the tensors hold the last
+        Small batches (warp-per-match kernel) run all the turns in ONE launch of evg_rollout's multi-turn kernel.  Above
+        that, a turn is one fused launch, and since mid-size batches are still launch-bound the turns are captured once
+        into a CUDA graph of `graph_turns` turns and replayed; what is left over runs as plain launches.  Results are those of calling step_agents(agent0, agent1) `turns` times: the tensors hold the last
         turn's outputs, episode statistics accumulate on the device.  graph_turns=0 disables the graph."""
         if not self._is_reset:
             raise RuntimeError("call reset() before rollout()")
@@ -230,6 +230,13 @@ class BatchedEvergladesEnv:
         if _capi.AGENT_EXTERNAL in (agent0, agent1):
             raise ValueError("rollout() needs both players scripted (AGENT_RANDOM / AGENT_BASE_RUSH / AGENT_SWARM)")
         left = int(turns)
+        if self._lib.evg_step_kernel_kind(self._h) == 0 and not (self.num_nodes > 15 and _capi.AGENT_RANDOM in (agent0, agent1)):
+            # small batch on the warp-per-match kernel: evg_rollout runs all the turns in ONE launch
+            _capi.check(self._lib.evg_rollout(self._h, agent0, agent1, left, C.c_void_p(self._actions.data_ptr()),
+                                              C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.reward.data_ptr()),
+                                              C.c_void_p(self.done.data_ptr()), C.c_void_p(self.status.data_ptr()),
+                                              C.c_void_p(self.scores.data_ptr()), self._stream()))
+            return self.obs, self.reward, self.done, {"status": self.status, "scores": self.scores}
         if graph_turns and left >= graph_turns:
             key = (agent0, agent1, int(graph_turns))
             graphs = self.__dict__.setdefault("_graphs", {})
@@ -286,7 +293,7 @@ class BatchedEvergladesEnv:
         it.  obs_format: 'f32' (the reference's vector, 840 B per match on DemoMap), 'i16' (same layout, 420 B) or
         'wire' (one packed 128-byte row per match that also carries reward and done; evgsim.wire.expand rebuilds the
         float32 vector exactly).  Returns the pinned host tensors (valid after the stream is synchronised; sync=True
-        does it).
+        does it); with 'wire' the reward and done tensors are views into the rows.
         """
         if not self._is_reset:
             raise RuntimeError("call reset() before step()")
@@ -302,20 +309,27 @@ class BatchedEvergladesEnv:
                 src.copy_(self._to_int8_rows(actions, "cpu"))
         rows = self.obs_rows(obs_format)
         scratch = C.c_void_p(self.obs.data_ptr()) if fmt == _capi.OBS_I16 else None
+        wire = fmt == _capi.OBS_WIRE  # the row carries the rewards and the done flag: no separate copies
         _capi.check(self._lib.evg_step_host_fmt(
             self._h, fmt, C.c_void_p(src.data_ptr()), C.c_void_p(hb["obs"].data_ptr()),
-            C.c_void_p(hb["reward"].data_ptr()), C.c_void_p(hb["done"].data_ptr()),
+            None if wire else C.c_void_p(hb["reward"].data_ptr()), None if wire else C.c_void_p(hb["done"].data_ptr()),
             C.c_void_p(self._actions.data_ptr()), C.c_void_p(rows.data_ptr()), scratch,
             C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), self._stream()))
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
+        if wire:
+            g = _capi.WIRE_NODE0 + 4 * self.num_nodes + 3 * 2 * _capi.NUM_GROUPS
+            rew = hb["obs"][:, g:g + 8].view(torch.float32)  # views into the pinned rows: [N,2] float32, [N] uint8
+            return hb["obs"], rew, hb["obs"][:, 2], {}
         return hb["obs"], hb["reward"], hb["done"], {}
 
     def h2d_bytes_per_step(self) -> int:
         return self.num_envs * int(self.layout.action_bytes)
 
     def d2h_bytes_per_step(self, obs_format="f32") -> int:
-        return self.num_envs * (int(self._lib.evg_obs_row_bytes(self._h, self._fmt(obs_format))) + 2 * 4 + 1)
+        fmt = self._fmt(obs_format)
+        extra = 0 if fmt == _capi.OBS_WIRE else 2 * 4 + 1  # separate reward and done copies (a wire row has them inside)
+        return self.num_envs * (int(self._lib.evg_obs_row_bytes(self._h, fmt)) + extra)
 
     # ------------------------------------------------------------------ scripted agents on the device
     def random_actions(self, player=-1, out=None):

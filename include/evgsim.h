@@ -231,6 +231,14 @@ int evg_step(EvgSim* sim, const int8_t* d_actions, float* d_obs, float* d_reward
 int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_actions, float* d_obs, float* d_reward,
                     uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream);
 
+/* `n_turns` turns of fully scripted self-play (both agents != EVG_AGENT_EXTERNAL) with the results of evg_step_agents
+ * called n_turns times: the output arrays hold the last turn's values, statistics accumulate, d_actions (required) is
+ * scratch for the generated rows.  Small batches (evg_step_kernel_kind() == 0) run ALL the turns in ONE launch — a warp
+ * keeps its match for the whole rollout, so a turn costs neither a launch nor an action-buffer pass; larger batches run
+ * one fused launch per turn (capture the call in a CUDA graph to shed the launch overhead). */
+int evg_rollout(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int32_t n_turns, int8_t* d_actions, float* d_obs, float* d_reward,
+                uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream);
+
 /* Same turn through HOST buffers: H2D of the actions, the step, D2H of obs/reward/done, ordered after
  * what `stream` holds and complete when `stream` is (pinned host memory makes them truly asynchronous).
  * The device staging arrays are the caller's (same shapes as evg_step).  From 65,536 matches on, the

@@ -111,7 +111,7 @@ def test_step_host_compact_formats_through_the_chunk_pipeline(evg, cfg, fmt):
         else:
             assert bool((rows.to(torch.float32) == bobs.cpu()).all()), t
         assert bool((rew == brew.cpu()).all()) and bool((done == bdone.cpu()).all()), t
-    assert a.d2h_bytes_per_step(fmt) == n * ({"wire": 128, "i16": 420}[fmt] + 9)
+    assert a.d2h_bytes_per_step(fmt) == n * {"wire": 128, "i16": 420 + 9}[fmt]
 
 
 def test_wire_with_fused_agents_takes_the_runtime_sized_kernel(evg, cfg, monkeypatch):
