@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=450)   # 3 full 150-turn episodes
     ap.add_argument("--warmup", type=int, default=150)  # 1 episode
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--total-envs", type=int, default=0,
+                    help="strong scaling: this many matches in total, split evenly over the ranks (overrides --envs-per-gpu)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=0)
@@ -284,6 +286,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.scaling = "weak"
+    if args.total_envs:
+        assert args.total_envs % (world * 128) == 0, "--total-envs must split into whole 128-match blocks per rank"
+        args.envs_per_gpu = args.total_envs // world
+        args.scaling = "strong"
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
@@ -438,7 +445,7 @@ def main():
         d2h = env.d2h_bytes_per_step(args.e2e_format)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "i32/f64", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step() * world,

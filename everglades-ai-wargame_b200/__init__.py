@@ -22,7 +22,7 @@ def __getattr__(name):  # torch is imported only when an env class is first used
     if name in ("EvergladesEnv", "BatchedEvergladesEnv", "MAX_SCORE"):
         from . import env as _env
         return getattr(_env, name)
-    if name in ("wire", "hostmem", "spaces"):
+    if name in ("wire", "hostmem", "spaces", "policy"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name == "register":

@@ -24,6 +24,7 @@ SHAPE_NORMALIZED_SCORE, SHAPE_BASIC, SHAPE_PENALIZE_LONG, SHAPE_SHORT_GAMES = 0,
 AGENT_EXTERNAL, AGENT_RANDOM, AGENT_BASE_RUSH, AGENT_SWARM = 0, 1, 2, 3
 OBS_F32, OBS_I16, OBS_WIRE = 0, 1, 2
 WIRE_NODE0 = 4
+MLP_IN_PAD, MLP_CHUNK, MLP_OUT_PAD = 128, 192, 144
 BIND_RECORDS, BIND_HEALTH, BIND_STATS, BIND_TABLES, BIND_AGENTS, BIND_COUNT = 0, 1, 2, 3, 4, 5
 
 _N1 = MAX_NODES + 1
@@ -165,6 +166,7 @@ SYMBOLS = [
     ("evg_agents", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_decode_dqn", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_decode_indices", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    ("evg_policy_mlp", C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("evg_shape_reward", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     ("evg_step_kernel_kind", C.c_int, [_P]),
     ("evg_launch_count", C.c_int64, [_P]),

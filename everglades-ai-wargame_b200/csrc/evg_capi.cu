@@ -60,6 +60,7 @@ struct EvgSim {
     size_t tpm_smem;
     int tpm_grid;     // persistent CTAs: SMs x resident CTAs
     int tpm_threads;  // 128, or 32 (one warp per CTA) for small batches
+    int sm_count;
 };
 
 namespace {
@@ -337,6 +338,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     int tpm_per_sm = 0;
     if ((e = evg::tpm_prepare(t, s->tpm_threads, &s->tpm_smem, &tpm_per_sm)) != cudaSuccess || tpm_per_sm < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
     s->tpm_grid = prop.multiProcessorCount * tpm_per_sm;
+    s->sm_count = prop.multiProcessorCount;
     if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
     int per_sm = 0;
     if ((e = evg::step_occupancy(t, s->smem, &per_sm)) != cudaSuccess || per_sm < 1) { delete s; return cuda_fail(e, "occupancy query"); }
@@ -352,7 +354,7 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.action_bytes = 2 * EVG_MAX_ACTIONS * 2;
     L.records_bytes = n_envs * L.record_bytes;
     L.health_bytes = n_envs * (int64_t)L.health_slots * 8;
-    L.stats_bytes = (evg::ST_COUNT + evg::kSchedSlots) * 8;  // + the step kernel's batch hand-out counters
+    L.stats_bytes = (evg::ST_COUNT + evg::kSchedSlots + 1) * 8;  // + the step kernel's batch hand-out counters + evg_import_state's error counter
     L.agents_bytes = n_envs * 16;
     // loss table, then reciprocals, then the Tables struct itself (the step kernel stages it from here)
     L.tables_bytes = round_up((int)((int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8), 16) + round_up((int)sizeof(evg::Tables), 16);
@@ -727,10 +729,20 @@ int evg_import_state(EvgSim* sim, int64_t first, int64_t count, const EvgEnvStat
     int rc = check_sim(sim, true);
     if (rc) return rc;
     if (!d_states || first < 0 || count < 0 || first + count > sim->n_envs) return fail(EVG_E_ARG, "evg_import_state: bad range [%lld,+%lld)", (long long)first, (long long)count);
-    cudaError_t e = evg::launch_import(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], first, count,
-                                       d_states, (cudaStream_t)stream);
+    // The kernel forces out-of-range fields (a location outside 1..n_nodes, a control state beyond the node's
+    // ControlPoints, ...) into range — they would index shared memory in the step kernels — and counts such records;
+    // the count is read back here (this entry point is a test / checkpoint path: it synchronises `stream`).
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* bad = (unsigned*)((unsigned long long*)sim->bound[EVG_BIND_STATS] + evg::kImportBadSlot);
+    cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    e = evg::launch_import(sim->tables, (uint32_t*)sim->bound[EVG_BIND_RECORDS], (double*)sim->bound[EVG_BIND_HEALTH], first, count, d_states, bad, st);
     if (e != cudaSuccess) return cuda_fail(e, "evg_import_kernel launch");
     sim->launches += count > 0;
+    unsigned h_bad = 0;
+    if ((e = cudaMemcpyAsync(&h_bad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H import check");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    if (h_bad) return fail(EVG_E_ARG, "evg_import_state: %u field group(s) out of range (location 1..n_nodes, destination <= n_nodes, |controlState| <= ControlPoints, controlledBy -1..1); they were forced into range", h_bad);
     return EVG_OK;
 }
 
@@ -809,6 +821,22 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
     if (!d_idx || !d_actions || div < 1 || mod < 1 || player < -1 || player > 1) return fail(EVG_E_ARG, "evg_decode_indices: bad argument");
     cudaError_t e = evg::launch_decode_indices(d_idx, div, mod, player, d_actions, sim->n_envs, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_decode_indices_kernel launch");
+    sim->launches += 1;
+    return EVG_OK;
+}
+
+int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const float* d_b1, const void* d_w2_img,
+                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, void* stream)
+{
+    int rc = check_sim(sim, false);
+    if (rc) return rc;
+    if (!d_obs || !d_w1_img || !d_b1 || !d_w2_img || !d_b2 || !d_q || rows < 0) return fail(EVG_E_ARG, "evg_policy_mlp: null argument");
+    if (sim->layout.obs_len > EVG_MLP_IN_PAD) return fail(EVG_E_ARG, "evg_policy_mlp: observations of %d values exceed the %d the kernel is tiled for", sim->layout.obs_len, EVG_MLP_IN_PAD);
+    if (hidden < 1 || hidden > 64 * EVG_MLP_CHUNK || out_dim < 1 || out_dim > EVG_MLP_OUT_PAD) return fail(EVG_E_ARG, "evg_policy_mlp: hidden %d / out_dim %d outside the kernel's tiling (out <= %d)", hidden, out_dim, EVG_MLP_OUT_PAD);
+    if (((uintptr_t)d_w1_img | (uintptr_t)d_w2_img) % 16) return fail(EVG_E_ARG, "evg_policy_mlp: weight images must be 16-byte aligned");
+    const int n_chunks = (hidden + EVG_MLP_CHUNK - 1) / EVG_MLP_CHUNK;
+    cudaError_t e = evg::launch_policy_mlp(d_obs, rows, sim->layout.obs_len, d_w1_img, d_b1, d_w2_img, d_b2, n_chunks, out_dim, d_q, sim->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evg_policy_mlp_kernel launch");
     sim->launches += 1;
     return EVG_OK;
 }

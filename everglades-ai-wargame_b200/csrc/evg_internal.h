@@ -109,6 +109,7 @@ constexpr int kTpmStage = EVG_TPM_STAGE;  // observation staging window per matc
 // the step's algorithmic bytes is 16 B per such slot, so bench.py can state it for the turns it timed
 enum { ST_EPISODES = 0, ST_WIN0, ST_WIN1, ST_TIES, ST_TURNS, ST_SCORE0, ST_SCORE1, ST_STATUS0, ST_FOUGHT = ST_STATUS0 + 4, ST_COUNT };
 constexpr int kSchedSlots = 2;  // behind the statistics in the same bound array: one counter pair (8 bytes) per concurrent launch
+constexpr int kImportBadSlot = ST_COUNT + kSchedSlots;  // then: records evg_import_state had to force into range (uint32)
 
 struct StepArgs {
     uint32_t* records;
@@ -150,11 +151,13 @@ cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t sme
 cudaError_t launch_rollout(const Tables& t, const StepArgs& a, int n_turns, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, void* obs, int obs_fmt,
                          int64_t n_envs, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const float* b1, const void* w2_img, const float* b2,
+                              int n_chunks, int out_dim, float* q, int sm_count, cudaStream_t stream);
 cudaError_t launch_obs_to_i16(const float* obs, int16_t* out, int64_t n_values, cudaStream_t stream);
 cudaError_t launch_export(const Tables& t, const uint32_t* records, const double* health, int64_t first, int64_t count,
                           EvgEnvState* out, cudaStream_t stream);
 cudaError_t launch_import(const Tables& t, uint32_t* records, double* health, int64_t first, int64_t count,
-                          const EvgEnvState* in, cudaStream_t stream);
+                          const EvgEnvState* in, unsigned* bad, cudaStream_t stream);
 cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t* actions, int player, int64_t n_envs,
                                 cudaStream_t stream);
 cudaError_t launch_decode_dqn(const float* q, int num_cols, int player, int8_t* actions, int64_t n_envs, cudaStream_t stream);

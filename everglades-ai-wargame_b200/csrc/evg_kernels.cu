@@ -683,7 +683,7 @@ __global__ void evg_export_kernel(const __grid_constant__ Tables T, const uint32
 }
 
 __global__ void evg_import_kernel(const __grid_constant__ Tables T, uint32_t* records, double* health, int64_t first, int64_t count,
-                                  const EvgEnvState* in)
+                                  const EvgEnvState* in, unsigned* bad)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -693,8 +693,19 @@ __global__ void evg_import_kernel(const __grid_constant__ Tables T, uint32_t* re
     for (int k = kRecGroupWords; k < T.rec_words8 * 2; ++k) rec[k] = 0;
     rec[kRecTurn] = (uint32_t)s->turn;
     rec[kRecEpisode] = (uint32_t)s->episode;
-    for (int n = 1; n <= T.n_nodes; ++n)
-        rec[kRecNode0 + n - 1] = ((uint32_t)s->control_state[n] & 0xFFFFu) | ((uint32_t)s->controlled_by[n] & 0xFFu) << 16;
+    for (int n = 1; n <= T.n_nodes; ++n) {
+        int cs = s->control_state[n], cb = s->controlled_by[n];
+        const int cp = T.node_cp[n];
+        if (cs > cp || cs < -cp || cb < -1 || cb > 1) {  // |controlState| <= ControlPoints, controlledBy in {-1, 0, 1}
+            cs = cs > cp ? cp : (cs < -cp ? -cp : cs);
+            cb = cb < -1 || cb > 1 ? -1 : cb;
+            atomicAdd(bad, 1u);
+        }
+        rec[kRecNode0 + n - 1] = ((uint32_t)cs & 0xFFFFu) | ((uint32_t)cb & 0xFFu) << 16;
+    }
+    // unit slots between the groups' sizes and their 4-slot padding are read by the step kernels as part of 32-byte
+    // quads: they hold 0.0 like every dead unit
+    for (int i = 0; i < T.health_slots; ++i) health[env * T.health_slots + i] = 0.0;
     for (int L = 0; L < kGroupLanes; ++L) {
         const EvgGroupState* g = &s->groups[L / EVG_NUM_GROUPS][L % EVG_NUM_GROUPS];
         double* hp = health + env * T.health_slots + T.g_slot[L];
@@ -709,8 +720,17 @@ __global__ void evg_import_kernel(const __grid_constant__ Tables T, uint32_t* re
         }
         // the cached observation field is derived state: recompute it (server.py:480-491)
         const int avg = alive ? (int)__ddiv_rn(np_pairwise_sum(tmp, size), (double)__popc(alive)) : 0;
-        const uint32_t dest = g->travel_destination > 0 ? (uint32_t)g->travel_destination & 0x3Fu : 0u;
-        rec[2 * L] = ((uint32_t)g->location & W0_LOC_MASK) | dest << W0_DEST_SHIFT |
+        // Out-of-range fields would become shared-memory indices in the step kernels: they are forced into range here
+        // (location 1..n_nodes, destination 0..n_nodes) and the record is counted in `bad`, which evg_import_state
+        // turns into EVG_E_ARG.  BatchedEvergladesEnv.set_state validates on the host before it gets this far.
+        int loc = g->location, dst = g->travel_destination > 0 ? g->travel_destination : 0;
+        if (loc < 1 || loc > T.n_nodes || dst > T.n_nodes || g->distance_remaining < 0 || g->distance_remaining > 255) {
+            loc = loc < 1 ? 1 : (loc > T.n_nodes ? T.n_nodes : loc);
+            dst = dst > T.n_nodes ? 0 : dst;
+            atomicAdd(bad, 1u);
+        }
+        const uint32_t dest = (uint32_t)dst & 0x3Fu;
+        rec[2 * L] = ((uint32_t)loc & W0_LOC_MASK) | dest << W0_DEST_SHIFT |
                      ((uint32_t)g->distance_remaining & 0xFFu) << W0_DIST_SHIFT | (g->ready ? W0_READY : 0u) |
                      (g->moving ? W0_MOVING : 0u) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT;
         rec[2 * L + 1] = alive | (((uint32_t)g->arrival >> 4) & 0xFFFFu) << 16;
@@ -950,10 +970,10 @@ cudaError_t launch_export(const Tables& t, const uint32_t* records, const double
 }
 
 cudaError_t launch_import(const Tables& t, uint32_t* records, double* health, int64_t first, int64_t count,
-                          const EvgEnvState* in, cudaStream_t stream)
+                          const EvgEnvState* in, unsigned* bad, cudaStream_t stream)
 {
     if (count <= 0) return cudaSuccess;
-    evg_import_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(t, records, health, first, count, in);
+    evg_import_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(t, records, health, first, count, in, bad);
     return cudaGetLastError();
 }
 

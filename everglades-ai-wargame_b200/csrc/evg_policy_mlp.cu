@@ -1,0 +1,274 @@
+// evg_policy_mlp.cu — the policy-in-the-loop forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// The only contraction on any configuration's path (BASELINE.json configs[3]): DQN's
+//     Q = Linear(105, 528) - ReLU - Linear(528, 132)          agents/DQN/QNetwork.py:37,42
+// evaluated for every (match, player) row of the observation tensor the step kernel has just written.  One kernel does
+// both layers; the hidden activations never leave the SM:
+//
+//   CTA = 128 threads = one tile of 128 observation rows (UMMA M = 128: TMEM lane i holds row i of the accumulators).
+//   per tile:  A  <- the tile's float32 observations, converted to bf16 into the K-major 128-byte-swizzled layout
+//              for each chunk c of 192 hidden units (528 -> 3 chunks, zero padded):
+//                 W1c, W2c <- the chunk's weight images (bf16, already in the swizzled shared-memory layout: a linear copy)
+//                 D1[128 x 192]  = A[128 x 128] . W1c^T          8 x tcgen05.mma  (K = 16 each), accumulators in TMEM
+//                 H              = bf16(relu(D1 + b1c))          tcgen05.ld -> registers -> swizzled shared memory
+//                 D2[128 x 144] += H[128 x 192] . W2c^T          12 x tcgen05.mma, accumulating over the chunks in TMEM
+//              Q rows <- D2 + b2                                   tcgen05.ld -> registers -> global (float32)
+//   One elected thread issues the MMAs and commits them to an mbarrier (tcgen05.commit); the CTA waits on it.
+//
+// bf16 operands, fp32 accumulation.  The decode of Q into action rows stays evg_decode_dqn (pinned to the reference's
+// DQNAgent.filter_actions); tests/test_gpu_policy.py checks Q against torch fp32 within the bf16 tolerance stated there.
+// Weight images are built on the host by evgsim.policy.pack_mlp (same swizzle function as below).
+#include <cuda_bf16.h>
+
+#include "evg_internal.h"
+
+namespace evg {
+
+namespace {
+
+constexpr int kMlpThreads = 128;
+constexpr int kTileM = 128;   // observation rows per tile
+constexpr int kInPad = 128;   // input features, padded (obs_len <= 128)
+constexpr int kChunk = 192;   // hidden units per chunk: 3 swizzle atoms of 64
+constexpr int kOutPad = 144;  // outputs, padded to a multiple of 16 (12 groups x 11 nodes = 132)
+constexpr int kAtomK = 64;    // bf16 elements in one 128-byte swizzle row
+
+// shared-memory carve-up (bytes; every operand block starts on a 1024-byte boundary, as the 128-byte swizzle needs)
+constexpr int kSmA = 0;                                            // 2 atoms x [128 rows x 128 B]
+constexpr int kSmH = kSmA + (kInPad / kAtomK) * kTileM * 128;      // 3 atoms x [128 rows x 128 B]
+constexpr int kSmW1 = kSmH + (kChunk / kAtomK) * kTileM * 128;     // 2 atoms x [192 rows x 128 B]
+constexpr int kSmW2 = kSmW1 + (kInPad / kAtomK) * kChunk * 128;    // 3 atoms x [144 rows x 128 B]
+constexpr int kSmBar = kSmW2 + (kChunk / kAtomK) * kOutPad * 128;  // 2 mbarriers + the TMEM base address
+constexpr int kSmBytes = kSmBar + 32;
+constexpr int kW1ChunkBytes = (kInPad / kAtomK) * kChunk * 128;    // 49152
+constexpr int kW2ChunkBytes = (kChunk / kAtomK) * kOutPad * 128;   // 55296
+static_assert(kSmH % 1024 == 0 && kSmW1 % 1024 == 0 && kSmW2 % 1024 == 0 && (kOutPad * 128) % 1024 == 0 && (kChunk * 128) % 1024 == 0, "swizzle atoms must be 1024-byte aligned");
+
+constexpr int kTmemCols = 512;  // power of two >= D1 (192) + D2 (144) columns
+constexpr int kTmemD1 = 0, kTmemD2 = 256;
+
+// K-major operand tile with 128-byte swizzle: element (row r, column k) of a [rows x K] bf16 matrix lives in atom k / 64
+// (a block of rows x 128 bytes), at row r, 16-byte chunk ((k % 64) / 8) ^ (r % 8)
+__host__ __device__ inline int swz_offset(int rows, int r, int k)
+{
+    return (k / kAtomK) * rows * 128 + r * 128 + ((((k % kAtomK) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 [0:14), leading byte offset >> 4
+// [16:30) (unused for a swizzled K-major operand), stride byte offset >> 4 [32:46) = 1024 B between 8-row groups,
+// version 1 [46:48), layout SWIZZLE_128B = 2 [61:64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (uint64_t)1 << 16 | (uint64_t)(1024 >> 4) << 32 | (uint64_t)1 << 46 | (uint64_t)2 << 61;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4:6) = 1, A bf16 [7:10) = 1, B bf16 [10:13) = 1, both
+// K-major, N >> 3 at [17:23), M >> 4 at [24:29)
+__device__ __forceinline__ uint32_t make_idesc(int m, int n)
+{
+    return 1u << 4 | 1u << 7 | 1u << 10 | (uint32_t)(n >> 3) << 17 | (uint32_t)(m >> 4) << 24;
+}
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// wait for phase `parity` of an mbarrier; a bounded spin that traps instead of hanging the GPU if the MMAs never arrive
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(kMlpThreads, 1)
+evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, const uint4* __restrict__ w1_img, const float* __restrict__ b1,
+                      const uint4* __restrict__ w2_img, const float* __restrict__ b2, int n_chunks, int out_dim, float* __restrict__ q)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmBar);  // [0]: layer-1 MMAs of a chunk done, [1]: layer-2 MMAs done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 16);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // one warp allocates the tensor memory (and frees it at the end)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes = rows 32 * warp ...
+    const uint32_t idesc1 = make_idesc(kTileM, kChunk), idesc2 = make_idesc(kTileM, kOutPad);
+    const uint32_t sA = smem_u32(smem + kSmA), sH = smem_u32(smem + kSmH), sW1 = smem_u32(smem + kSmW1), sW2 = smem_u32(smem + kSmW2);
+    uint32_t ph0 = 0, ph1 = 0;
+    const int64_t n_tiles = (rows + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kTileM;
+        const int nrows = rows - row0 < kTileM ? (int)(rows - row0) : kTileM;
+        // ---- A: the tile's observations (contiguous in memory) -> bf16, swizzled; padding rows / columns are zero
+        {
+            uint4* a4 = reinterpret_cast<uint4*>(smem + kSmA);
+            for (int i = tid; i < (kInPad / kAtomK) * kTileM * 8; i += kMlpThreads) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+            const float* src = obs + row0 * in_dim;
+            const int total = nrows * in_dim;
+            for (int i = tid; i < total; i += kMlpThreads) {
+                const int r = i / in_dim, k = i - r * in_dim;
+                *reinterpret_cast<__nv_bfloat16*>(smem + kSmA + swz_offset(kTileM, r, k)) = __float2bfloat16_rn(__ldcs(src + i));
+            }
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            // ---- this chunk's weight images: linear 16-byte copies (they are L2 residents: every CTA reads the same 300 KB)
+            {
+                const uint4* g1 = w1_img + (size_t)c * (kW1ChunkBytes / 16);
+                uint4* s1 = reinterpret_cast<uint4*>(smem + kSmW1);
+                for (int i = tid; i < kW1ChunkBytes / 16; i += kMlpThreads) s1[i] = __ldg(g1 + i);
+                const uint4* g2 = w2_img + (size_t)c * (kW2ChunkBytes / 16);
+                uint4* s2 = reinterpret_cast<uint4*>(smem + kSmW2);
+                for (int i = tid; i < kW2ChunkBytes / 16; i += kMlpThreads) s2[i] = __ldg(g2 + i);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+            __syncthreads();
+            // ---- layer 1: D1 = A . W1c^T
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < kInPad / 16; ++k) {  // within a swizzle atom the start address advances by 32 bytes per K = 16
+                    const uint32_t offA = (k >> 2) * (kTileM * 128) + (k & 3) * 32, offB = (k >> 2) * (kChunk * 128) + (k & 3) * 32;
+                    umma(tmem + kTmemD1, make_desc(sA + offA), make_desc(sW1 + offB), idesc1, k > 0);
+                }
+                umma_commit(&bar[0]);
+            }
+            mbar_wait(&bar[0], ph0);
+            ph0 ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- hidden activations of my row: TMEM -> registers -> bias, ReLU, bf16 -> swizzled H
+            {
+                const int r = tid;
+                const float* bc = b1 + c * kChunk;
+#pragma unroll 1
+                for (int j0 = 0; j0 < kChunk; j0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + kTmemD1 + j0, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {  // 8 hidden units = one 16-byte chunk of the swizzled row
+                        float h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) h[e] = fmaxf(__uint_as_float(v[8 * g + e]) + __ldg(bc + j0 + 8 * g + e), 0.f);
+                        const int k = j0 + 8 * g;
+                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, k)) =
+                            make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            // ---- layer 2: D2 += H . W2c^T
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < kChunk / 16; ++k) {
+                    const uint32_t offA = (k >> 2) * (kTileM * 128) + (k & 3) * 32, offB = (k >> 2) * (kOutPad * 128) + (k & 3) * 32;
+                    umma(tmem + kTmemD2, make_desc(sH + offA), make_desc(sW2 + offB), idesc2, (c > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&bar[1]);
+            }
+            mbar_wait(&bar[1], ph1);  // H and the weight buffers are free again; after the last chunk D2 is complete
+            ph1 ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        // ---- Q = D2 + b2, my row
+        {
+            const int r = tid;
+            float* qr = q + (row0 + r) * out_dim;
+#pragma unroll 1
+            for (int j0 = 0; j0 < kOutPad; j0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_base + kTmemD2 + j0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (r < nrows) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (j0 + e < out_dim) qr[j0 + e] = __uint_as_float(v[e]) + __ldg(b2 + j0 + e);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // the next tile's first MMAs overwrite D1 / D2, its loads overwrite A
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+}  // namespace
+
+cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const float* b1, const void* w2_img, const float* b2,
+                              int n_chunks, int out_dim, float* q, int sm_count, cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(evg_policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int64_t tiles = (rows + kTileM - 1) / kTileM;
+    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
+    evg_policy_mlp_kernel<<<grid, kMlpThreads, kSmBytes, stream>>>(obs, rows, in_dim, reinterpret_cast<const uint4*>(w1_img), b1,
+                                                                   reinterpret_cast<const uint4*>(w2_img), b2, n_chunks, out_dim, q);
+    return cudaGetLastError();
+}
+
+}  // namespace evg

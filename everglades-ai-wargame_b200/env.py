@@ -394,10 +394,24 @@ class BatchedEvergladesEnv:
         return buf.cpu().numpy().view(dt).copy()
 
     def set_state(self, states, first=0):
+        """Import EvgEnvState records (get_state's dtype) into matches [first, first+len).  Before the first reset() only
+        an import that covers ALL matches is accepted (the others would be uninitialised memory); fields that the
+        kernels use as indices are validated here and raise ValueError."""
         torch = _torch()
         dt = _capi.env_state_dtype()
         states = np.ascontiguousarray(states)
         assert states.dtype == dt
+        if not self._is_reset and not (first == 0 and len(states) == self.num_envs):
+            raise RuntimeError("set_state() before reset() must cover all %d matches" % self.num_envs)
+        n = self.num_nodes
+        g = states["groups"]
+        cp = np.array(list(self.cfg.node_control_points)[:n + 1])
+        if ((g["location"] < 1) | (g["location"] > n)).any() or (g["travel_destination"] > n).any() \
+                or ((g["distance_remaining"] < 0) | (g["distance_remaining"] > 255)).any() \
+                or (np.abs(states["control_state"][:, 1:n + 1].astype(np.int64)) > cp[1:]).any() \
+                or ((states["controlled_by"][:, 1:n + 1] < -1) | (states["controlled_by"][:, 1:n + 1] > 1)).any():
+            raise ValueError("set_state: location must be 1..%d, travel_destination <= %d, distance_remaining 0..255, "
+                             "|control_state| <= ControlPoints and controlled_by -1..1" % (n, n))
         buf = torch.from_numpy(states.view(np.uint8).reshape(-1).copy()).to(self.device)
         _capi.check(self._lib.evg_import_state(self._h, first, len(states), C.c_void_p(buf.data_ptr()), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()

@@ -265,6 +265,10 @@ int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void
 /* Array-of-structs snapshot <-> resident layout, matches [first, first+count).  d_states is a
  * DEVICE array of EvgEnvState (the caller copies it to/from the host). */
 int evg_export_state(EvgSim* sim, int64_t first, int64_t count, EvgEnvState* d_states, void* stream);
+/* Import validates what it is given: a location outside 1..n_nodes, a travel_destination above n_nodes, a
+ * distance_remaining outside 0..255, |control_state| above the node's ControlPoints or a controlled_by outside -1..1 is
+ * forced into range (these fields index tables in the step kernels) and the call returns EVG_E_ARG after importing the
+ * rest.  Synchronises `stream`. */
 int evg_import_state(EvgSim* sim, int64_t first, int64_t count, const EvgEnvState* d_states, void* stream);
 
 /* Copy the statistics accumulators to the host (synchronises `stream`). */
@@ -288,6 +292,23 @@ int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_action
 int evg_decode_dqn(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int8_t* d_actions, void* stream);
 int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t mod, int32_t player, int8_t* d_actions,
                        void* stream);
+
+/* Policy-in-the-loop forward, fused on the tensor cores (tcgen05 + TMEM; csrc/evg_policy_mlp.cu):
+ *     d_q[rows][out_dim] = Linear(hidden, out_dim)(relu(Linear(obs_len, hidden)(d_obs[rows][obs_len])))
+ * — the reference's DQN network, agents/DQN/QNetwork.py:37,42 (105 -> 528 -> 132) — for the observation rows the step
+ * has just written (rows = n_envs * 2 for both players), bf16 operands with fp32 accumulation; the hidden activations stay
+ * on the SM.  Weights are passed as IMAGES in the kernel's shared-memory operand layout (bf16, K-major, 128-byte swizzle),
+ * cut into chunks of EVG_MLP_CHUNK hidden units: for chunk c,
+ *     d_w1_img + c * (EVG_MLP_IN_PAD / 64) * EVG_MLP_CHUNK * 128 bytes:  W1[c*CHUNK + n][k], n < CHUNK, k < IN_PAD
+ *     d_w2_img + c * (EVG_MLP_CHUNK / 64) * EVG_MLP_OUT_PAD * 128 bytes: W2[o][c*CHUNK + k], o < OUT_PAD, k < CHUNK
+ * element (row r, column k) of a [R x K] block at byte (k/64)*R*128 + r*128 + ((((k%64)/8) ^ (r%8)) * 16) + (k%8)*2, zero
+ * padded; d_b1 has ceil(hidden / CHUNK) * CHUNK floats (zero padded), d_b2 out_dim floats.  evgsim.policy.pack_mlp builds
+ * them from a torch module.  Decode d_q with evg_decode_dqn. */
+#define EVG_MLP_IN_PAD 128
+#define EVG_MLP_CHUNK 192
+#define EVG_MLP_OUT_PAD 144
+int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const float* d_b1, const void* d_w2_img,
+                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, void* stream);
 
 /* Reward shaping of the reference's training scripts (utils/reward_shaping.py:17-56) on the step's outputs:
  * d_out float32 [n_envs][2].  turnNum (steps played before this one) is read from the observation's turn

@@ -384,6 +384,39 @@ def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg, monke
         cfg.auto_reset = 0
 
 
+def test_import_rejects_out_of_range_fields(evg, cfg):
+    """Fields the step kernels use as indices are validated: BatchedEvergladesEnv.set_state raises on the host, the C
+    entry point forces them into range, reports EVG_E_ARG, and the simulator keeps stepping on sane state."""
+    import ctypes as C
+    import torch
+    env = evg.BatchedEvergladesEnv(64, seed=2, config=cfg)
+    with pytest.raises(RuntimeError):
+        env.set_state(np.zeros(3, dtype=evg._capi.env_state_dtype()))  # partial import before any reset
+    env.reset()
+    st = env.get_state()
+    for field, value in (("location", 0), ("location", 12), ("travel_destination", 40)):
+        bad = st.copy()
+        bad["groups"][field][5, 1, 3] = value
+        with pytest.raises(ValueError):
+            env.set_state(bad)
+    bad = st.copy()
+    bad["control_state"][7, 4] = 3000
+    with pytest.raises(ValueError):
+        env.set_state(bad)
+    # straight through the C ABI: imported with the field forced into range, and reported
+    bad = st.copy()
+    bad["groups"]["location"][9, 0, 0] = 63
+    buf = torch.from_numpy(bad.view(np.uint8).reshape(-1).copy()).to(env.device)
+    rc = env._lib.evg_import_state(env._h, 0, 64, C.c_void_p(buf.data_ptr()), None)
+    assert rc == evg._capi.E_ARG if hasattr(evg._capi, "E_ARG") else rc == -1
+    assert b"out of range" in env._lib.evg_last_error()
+    assert env.get_state()["groups"]["location"][9, 0, 0] == 11
+    for _ in range(5):
+        env.step(env.random_actions())
+    env.set_state(st)  # a valid snapshot still imports
+    assert_states_equal(env.get_state(), st, "re-import")
+
+
 @pytest.mark.parametrize("n", [600, 16384 + 5])
 def test_rollout_from_a_cuda_graph_equals_plain_turns(evg, cfg, n):
     """BatchedEvergladesEnv.rollout replays the self-play turn from a CUDA graph (50 turns per replay + a remainder of

@@ -8,5 +8,5 @@ name=$1; shift
 mkdir -p build
 C=everglades-ai-wargame_b200/csrc
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" \
-    -o build/libevgsim_$name.so $C/evg_kernels.cu $C/evg_step_tpm.cu $C/evg_capi.cu
+    -o build/libevgsim_$name.so $C/evg_kernels.cu $C/evg_step_tpm.cu $C/evg_policy_mlp.cu $C/evg_capi.cu
 echo built build/libevgsim_$name.so

@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3]: PyTorch policy-in-the-loop self-play rollout.
 
-    python tools/policy_rollout.py [--envs-per-gpu 32768] [--turns 300] [--policy dqn|ppo] [--dtype fp32|bf16]
+    python tools/policy_rollout.py [--envs-per-gpu 32768] [--turns 300] [--policy dqn|ppo|rppo] [--dtype fp32|bf16] [--graph]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/policy_rollout.py
 
 Both players are driven by one network of the reference's shape — DQN: Linear(105, 528) - ReLU - Linear(528, 132)
 (agents/DQN/QNetwork.py:37-42, random weights), decoded like DQNAgent.filter_actions (evg_decode_dqn); PPO: the
 actor's Linear(105, 128) - Tanh - Linear(128, 128) - Tanh - Linear(128, 132) - Tanh - Softmax head
 (agents/PPO/ActorCritic.py:33-50, without the GRU), 7 indices sampled without replacement and unravelled like
-PPOAgent.get_action (evg_decode_indices).  The observation tensor the step kernel writes is consumed in place
+PPOAgent.get_action (evg_decode_indices); RPPO: the same head, its output repeated 7 times through the actor's
+GRU(128, 128) (hidden state carried over the 7 steps and from turn to turn, zeroed when a match ends), one index
+sampled per step (ActorCritic.act with use_recurrent, agents/PPO/ActorCritic.py:79-105).  --graph captures the whole
+turn (forward, sampling, decode, step) in a CUDA graph.  The observation tensor the step kernel writes is consumed in place
 (a [N*2, 105] view, no copy, no dtype conversion kernel for fp32); the decoded int8 rows go straight back into the
 step.  Matches shard over the ranks with no collective on the path; rank 0 prints one JSON line.
 """
@@ -22,10 +25,27 @@ import torch
 import evgsim
 
 
+class RecurrentActor(torch.nn.Module):
+    """ActorCritic's actor with use_recurrent=True (agents/PPO/ActorCritic.py:33-50,79-105), batched over (match, player)."""
+
+    def __init__(self, n_latent=128):
+        super().__init__()
+        self.action_head = torch.nn.Sequential(torch.nn.Linear(105, n_latent), torch.nn.Tanh(), torch.nn.Linear(n_latent, n_latent), torch.nn.Tanh())
+        self.action_gru = torch.nn.GRU(n_latent, n_latent, batch_first=False)
+        self.action_layer = torch.nn.Sequential(torch.nn.Linear(n_latent, 132), torch.nn.Tanh(), torch.nn.Softmax(dim=-1))
+
+    def forward(self, x, hidden):
+        h = self.action_head(x)                                   # [B, 128]
+        seq, hidden = self.action_gru(h.unsqueeze(0).expand(7, -1, -1).contiguous(), hidden)  # the observation repeated for the 7 actions
+        return self.action_layer(seq), hidden                     # [7, B, 132], [1, B, 128]
+
+
 def build_policy(kind, dtype, device, seed=0):
     torch.manual_seed(seed)
     if kind == "dqn":
         net = torch.nn.Sequential(torch.nn.Linear(105, 528), torch.nn.ReLU(), torch.nn.Linear(528, 132))
+    elif kind == "rppo":
+        net = RecurrentActor()
     else:
         net = torch.nn.Sequential(torch.nn.Linear(105, 128), torch.nn.Tanh(), torch.nn.Linear(128, 128), torch.nn.Tanh(),
                                   torch.nn.Linear(128, 132), torch.nn.Tanh(), torch.nn.Softmax(dim=-1))
@@ -33,9 +53,15 @@ def build_policy(kind, dtype, device, seed=0):
 
 
 @torch.no_grad()
-def policy_actions(env, net, kind, dtype):
+def policy_actions(env, net, kind, dtype, hidden=None):
     x = env.obs.view(-1, env.obs_len)  # [N*2, 105], the step kernel's output buffer itself
-    out = net(x if dtype == torch.float32 else x.to(dtype))
+    x = x if dtype == torch.float32 else x.to(dtype)
+    if kind == "rppo":
+        probs, h = net(x, hidden)
+        hidden.copy_(h)
+        idx = torch.multinomial(probs.float().view(-1, 132), 1).view(7, env.num_envs, 2).permute(1, 2, 0).contiguous()
+        return env.decode_indices(idx, div=12, mod=11)
+    out = net(x)
     if kind == "dqn":
         return env.decode_dqn(out.float().view(env.num_envs, 2, -1))
     idx = torch.multinomial(out.float(), 7, replacement=False)  # PPOAgent.get_action draws 7 distinct flat indices
@@ -47,8 +73,9 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=32768)  # 262,144 over 8 GPUs
     ap.add_argument("--turns", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=150)
-    ap.add_argument("--policy", default="dqn", choices=["dqn", "ppo"])
+    ap.add_argument("--policy", default="dqn", choices=["dqn", "ppo", "rppo"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--graph", action="store_true", help="replay the turn (forward, decode, step) from a CUDA graph")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -62,15 +89,34 @@ def main():
     env = evgsim.BatchedEvergladesEnv(E, device=local, seed=0, auto_reset=evgsim._capi.AUTORESET_TERMINAL, env_id_offset=first)
     net = build_policy(args.policy, dtype, env.device)
     env.reset()
+    hidden = torch.zeros((1, 2 * E, 128), dtype=dtype, device=env.device) if args.policy == "rppo" else None
+
+    def turn():
+        env.step(policy_actions(env, net, args.policy, dtype, hidden))
+        if hidden is not None:  # a finished match starts over with a fresh hidden state
+            hidden.mul_((1 - env.done).to(dtype).repeat_interleave(2).view(1, -1, 1))
+
+    run = turn
+    if args.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                turn()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                turn()
+        torch.cuda.current_stream().wait_stream(side)
+        run = g.replay
     for _ in range(args.warmup):
-        env.step(policy_actions(env, net, args.policy, dtype))
+        run()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.turns):
-        env.step(policy_actions(env, net, args.policy, dtype))
+        run()
     b.record()
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=env.device)
@@ -79,7 +125,7 @@ def main():
     stats = evgsim.gather_episode_stats(env.episode_stats(), device=env.device) if world > 1 else env.episode_stats()
     if rank == 0:
         sec = float(ms.item()) / 1e3
-        print(json.dumps({"workload": "policy-in-the-loop self-play (BASELINE.json configs[3])", "policy": args.policy, "dtype": args.dtype,
+        print(json.dumps({"workload": "policy-in-the-loop self-play (BASELINE.json configs[3])", "policy": args.policy, "dtype": args.dtype, "cuda_graph": bool(args.graph),
                           "n_gpus": world, "envs_per_gpu": E, "turns": args.turns, "env_turns_per_s": E * world * args.turns / sec,
                           "ms_per_turn": sec * 1e3 / args.turns, "episodes": stats["episodes"], "wins": stats["wins"], "ties": stats["ties"]}))
     if world > 1:
