@@ -805,10 +805,15 @@ int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_action
 
 int evg_decode_dqn(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int8_t* d_actions, void* stream)
 {
+    return evg_decode_dqn_layout(sim, d_q, num_cols, player, 0, d_actions, stream);
+}
+
+int evg_decode_dqn_layout(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int32_t q_transposed, int8_t* d_actions, void* stream)
+{
     int rc = check_sim(sim, false);
     if (rc) return rc;
     if (!d_q || !d_actions || num_cols < 1 || num_cols > 127 || player < -1 || player > 1) return fail(EVG_E_ARG, "evg_decode_dqn: bad argument");
-    cudaError_t e = evg::launch_decode_dqn(d_q, num_cols, player, d_actions, sim->n_envs, (cudaStream_t)stream);
+    cudaError_t e = evg::launch_decode_dqn(d_q, num_cols, player, d_actions, sim->n_envs, q_transposed, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_decode_dqn_kernel launch");
     sim->launches += 1;
     return EVG_OK;
@@ -826,7 +831,7 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
 }
 
 int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const float* d_b1, const void* d_w2_img,
-                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, void* stream)
+                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, int32_t q_transposed, void* stream)
 {
     int rc = check_sim(sim, false);
     if (rc) return rc;
@@ -835,7 +840,7 @@ int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_
     if (hidden < 1 || hidden > 64 * EVG_MLP_CHUNK || out_dim < 1 || out_dim > EVG_MLP_OUT_PAD) return fail(EVG_E_ARG, "evg_policy_mlp: hidden %d / out_dim %d outside the kernel's tiling (out <= %d)", hidden, out_dim, EVG_MLP_OUT_PAD);
     if (((uintptr_t)d_w1_img | (uintptr_t)d_w2_img) % 16) return fail(EVG_E_ARG, "evg_policy_mlp: weight images must be 16-byte aligned");
     const int n_chunks = (hidden + EVG_MLP_CHUNK - 1) / EVG_MLP_CHUNK;
-    cudaError_t e = evg::launch_policy_mlp(d_obs, rows, sim->layout.obs_len, d_w1_img, d_b1, d_w2_img, d_b2, n_chunks, out_dim, d_q, sim->sm_count, (cudaStream_t)stream);
+    cudaError_t e = evg::launch_policy_mlp(d_obs, rows, sim->layout.obs_len, d_w1_img, d_b1, d_w2_img, d_b2, n_chunks, out_dim, d_q, q_transposed, sim->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_policy_mlp_kernel launch");
     sim->launches += 1;
     return EVG_OK;

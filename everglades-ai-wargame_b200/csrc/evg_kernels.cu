@@ -820,35 +820,48 @@ __global__ void evg_agents_kernel(const __grid_constant__ Tables T, const uint32
 // at 0; a group already placed in another slot may only improve its own slot; the node written is the 0-based
 // column (the reference's off-by-one).  One thread per (match, player); q is [rows][12 * num_cols] float32.
 // ---------------------------------------------------------------------------------------------
-__global__ void evg_decode_dqn_kernel(const float* q, int num_cols, int player, int8_t* actions, int64_t n_envs)
+// q[i * row_stride + c * col_stride] is entry c of row i: row-major network output (row_stride = 12 * num_cols, col_stride = 1)
+// or the transposed layout evg_policy_mlp writes (row_stride = 1, col_stride = rows), which this thread-per-row scan reads
+// coalesced.  Every slot's best-Q only ever grows, so a candidate that does not beat the smallest of them is skipped at once.
+__global__ void evg_decode_dqn_kernel(const float* __restrict__ q, int num_cols, int player, int8_t* actions, int64_t n_envs, int64_t row_stride,
+                                      int64_t col_stride)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int np_ = player < 0 ? 2 : 1;
     if (i >= n_envs * np_) return;
     const int64_t env = i / np_;
     const int p = player < 0 ? (int)(i % np_) : player;
-    const float* qi = q + i * (EVG_NUM_GROUPS * num_cols);
+    const float* qi = q + i * row_stride;
     float bq[EVG_MAX_ACTIONS];
     int bu[EVG_MAX_ACTIONS], bn[EVG_MAX_ACTIONS];
 #pragma unroll
     for (int s = 0; s < EVG_MAX_ACTIONS; ++s) { bq[s] = 0.f; bu[s] = 0; bn[s] = 0; }
-    for (int n = 0; n < num_cols; ++n)
+    float bmin = 0.f;
+    for (int n = 0; n < num_cols; ++n) {
+        float v[EVG_NUM_GROUPS];  // the twelve candidates of this node: independent loads in flight together
+#pragma unroll
+        for (int g = 0; g < EVG_NUM_GROUPS; ++g) v[g] = __ldcs(qi + (int64_t)(g * num_cols + n) * col_stride);
+#pragma unroll
         for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
-            const float v = qi[g * num_cols + n];
-            bool placed = false;
+            if (!(v[g] > bmin)) continue;
+            uint32_t eqm = 0, gtm = 0;  // slots that hold group g (`group_index in best_action_units`) / that v beats
 #pragma unroll
             for (int s = 0; s < EVG_MAX_ACTIONS; ++s) {
-                if (!placed && v > bq[s]) {
-                    bool in_units = false;  // `group_index in best_action_units`
+                eqm |= (bu[s] == g ? 1u : 0u) << s;
+                gtm |= (v[g] > bq[s] ? 1u : 0u) << s;
+            }
+            const uint32_t ok = eqm ? (gtm & eqm) : gtm;  // a group already placed may only improve its own slot
+            if (ok) {
+                const int s0 = __ffs(ok) - 1;  // the first slot in order that takes it
 #pragma unroll
-                    for (int k = 0; k < EVG_MAX_ACTIONS; ++k) in_units |= bu[k] == g;
-                    if (!(in_units && bu[s] != g)) {
-                        bq[s] = v; bu[s] = g; bn[s] = n;
-                        placed = true;
-                    }
-                }
+                for (int s = 0; s < EVG_MAX_ACTIONS; ++s)
+                    if (s == s0) { bq[s] = v[g]; bu[s] = g; bn[s] = n; }
+                bmin = bq[0];
+#pragma unroll
+                for (int s = 1; s < EVG_MAX_ACTIONS; ++s) bmin = fminf(bmin, bq[s]);
             }
         }
+    }
     uint16_t* out = reinterpret_cast<uint16_t*>(actions + (env * 2 + p) * (EVG_MAX_ACTIONS * 2));
 #pragma unroll
     for (int s = 0; s < EVG_MAX_ACTIONS; ++s) out[s] = (uint16_t)((uint32_t)bu[s] | (uint32_t)bn[s] << 8);
@@ -986,11 +999,12 @@ cudaError_t launch_agent_random(const Tables& t, const uint32_t* records, int8_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode_dqn(const float* q, int num_cols, int player, int8_t* actions, int64_t n_envs, cudaStream_t stream)
+cudaError_t launch_decode_dqn(const float* q, int num_cols, int player, int8_t* actions, int64_t n_envs, int transposed, cudaStream_t stream)
 {
     const int64_t n = n_envs * (player < 0 ? 2 : 1);
     if (n <= 0) return cudaSuccess;
-    evg_decode_dqn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(q, num_cols, player, actions, n_envs);
+    evg_decode_dqn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(q, num_cols, player, actions, n_envs,
+                                                                           transposed ? 1 : (int64_t)EVG_NUM_GROUPS * num_cols, transposed ? n : 1);
     return cudaGetLastError();
 }
 

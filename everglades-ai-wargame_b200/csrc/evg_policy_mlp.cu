@@ -5,18 +5,23 @@
 // evaluated for every (match, player) row of the observation tensor the step kernel has just written.  One kernel does
 // both layers; the hidden activations never leave the SM:
 //
-//   CTA = 128 threads = one tile of 128 observation rows (UMMA M = 128: TMEM lane i holds row i of the accumulators).
+//   CTA = 256 threads = one tile of 128 observation rows at a time (UMMA M = 128: TMEM lane i holds row i of the
+//   accumulators; two threads per row, one per half of the columns), persistent over the tiles.
 //   per tile:  A  <- the tile's float32 observations, converted to bf16 into the K-major 128-byte-swizzled layout
 //              for each chunk c of 192 hidden units (528 -> 3 chunks, zero padded):
-//                 W1c, W2c <- the chunk's weight images (bf16, already in the swizzled shared-memory layout: a linear copy)
 //                 D1[128 x 192]  = A[128 x 128] . W1c^T          8 x tcgen05.mma  (K = 16 each), accumulators in TMEM
 //                 H              = bf16(relu(D1 + b1c))          tcgen05.ld -> registers -> swizzled shared memory
 //                 D2[128 x 144] += H[128 x 192] . W2c^T          12 x tcgen05.mma, accumulating over the chunks in TMEM
-//              Q rows <- D2 + b2                                   tcgen05.ld -> registers -> global (float32)
-//   One elected thread issues the MMAs and commits them to an mbarrier (tcgen05.commit); the CTA waits on it.
+//              Q <- D2 + b2                                        tcgen05.ld -> registers -> global (float32)
+//   The weight chunks W1c / W2c are bf16 IMAGES of the shared-memory operand layout, fetched by the bulk-copy engine
+//   (cp.async.bulk, one instruction per 48 / 54 KB image, completion on an mbarrier) as soon as the MMAs that read the
+//   buffer's previous content have retired: W1(c+1) arrives under the activation epilogue and layer 2 of chunk c,
+//   W2(c+1) under layer 1 and the epilogue of chunk c+1.  One elected thread issues copies and MMAs and commits the
+//   MMAs to mbarriers (tcgen05.commit); the CTA waits on those.
 //
-// bf16 operands, fp32 accumulation.  The decode of Q into action rows stays evg_decode_dqn (pinned to the reference's
-// DQNAgent.filter_actions); tests/test_gpu_policy.py checks Q against torch fp32 within the bf16 tolerance stated there.
+// bf16 operands, fp32 accumulation.  Q is written either row-major [rows][out] (torch's layout) or transposed
+// [out][rows] — what the thread-per-row decode (evg_decode_dqn, pinned to the reference's DQNAgent.filter_actions)
+// reads coalesced.  tests/test_gpu_policy.py checks Q against torch fp32 within the bf16 tolerance stated there.
 // Weight images are built on the host by evgsim.policy.pack_mlp (same swizzle function as below).
 #include <cuda_bf16.h>
 
@@ -26,7 +31,7 @@ namespace evg {
 
 namespace {
 
-constexpr int kMlpThreads = 128;
+constexpr int kMlpThreads = 256;
 constexpr int kTileM = 128;   // observation rows per tile
 constexpr int kInPad = 128;   // input features, padded (obs_len <= 128)
 constexpr int kChunk = 192;   // hidden units per chunk: 3 swizzle atoms of 64
@@ -38,8 +43,8 @@ constexpr int kSmA = 0;                                            // 2 atoms x 
 constexpr int kSmH = kSmA + (kInPad / kAtomK) * kTileM * 128;      // 3 atoms x [128 rows x 128 B]
 constexpr int kSmW1 = kSmH + (kChunk / kAtomK) * kTileM * 128;     // 2 atoms x [192 rows x 128 B]
 constexpr int kSmW2 = kSmW1 + (kInPad / kAtomK) * kChunk * 128;    // 3 atoms x [144 rows x 128 B]
-constexpr int kSmBar = kSmW2 + (kChunk / kAtomK) * kOutPad * 128;  // 2 mbarriers + the TMEM base address
-constexpr int kSmBytes = kSmBar + 32;
+constexpr int kSmBar = kSmW2 + (kChunk / kAtomK) * kOutPad * 128;  // 4 mbarriers + the TMEM base address
+constexpr int kSmBytes = kSmBar + 48;
 constexpr int kW1ChunkBytes = (kInPad / kAtomK) * kChunk * 128;    // 49152
 constexpr int kW2ChunkBytes = (kChunk / kAtomK) * kOutPad * 128;   // 55296
 static_assert(kSmH % 1024 == 0 && kSmW1 % 1024 == 0 && kSmW2 % 1024 == 0 && (kOutPad * 128) % 1024 == 0 && (kChunk * 128) % 1024 == 0, "swizzle atoms must be 1024-byte aligned");
@@ -127,17 +132,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return *reinterpret_cast<const uint32_t*>(&p);
 }
 
+// one bulk copy global -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// q_col_stride == 1: Q[row * q_row_stride + col] (row-major); q_row_stride == 1: Q[col * q_col_stride + row] (transposed)
 __global__ void __launch_bounds__(kMlpThreads, 1)
-evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, const uint4* __restrict__ w1_img, const float* __restrict__ b1,
-                      const uint4* __restrict__ w2_img, const float* __restrict__ b2, int n_chunks, int out_dim, float* __restrict__ q)
+evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, const unsigned char* __restrict__ w1_img, const float* __restrict__ b1,
+                      const unsigned char* __restrict__ w2_img, const float* __restrict__ b2, int n_chunks, int out_dim, float* __restrict__ q,
+                      int64_t q_row_stride, int64_t q_col_stride)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmBar);  // [0]: layer-1 MMAs of a chunk done, [1]: layer-2 MMAs done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmBar);  // [0] layer-1 MMAs done, [1] layer-2 MMAs done, [2] W1 image landed, [3] W2 image landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 32);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // one warp allocates the tensor memory (and frees it at the end)
@@ -148,40 +164,55 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes = rows 32 * warp ...
+    // my row = TMEM lane 32 * (warp % 4) + lane (a warp reaches the lane quarter warp % 4); my half of the columns = warp / 4
+    const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc1 = make_idesc(kTileM, kChunk), idesc2 = make_idesc(kTileM, kOutPad);
     const uint32_t sA = smem_u32(smem + kSmA), sH = smem_u32(smem + kSmH), sW1 = smem_u32(smem + kSmW1), sW2 = smem_u32(smem + kSmW2);
-    uint32_t ph0 = 0, ph1 = 0;
     const int64_t n_tiles = (rows + kTileM - 1) / kTileM;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_steps = my_tiles * n_chunks;  // (tile, chunk) steps of this CTA: the weight images cycle through the chunks
+    uint32_t ph_m1 = 0, ph_m2 = 0, ph_w1 = 0, ph_w2 = 0;
+    if (tid == 0 && n_steps > 0) {
+        bulk_load(smem + kSmW1, w1_img, kW1ChunkBytes, &bar[2]);
+        bulk_load(smem + kSmW2, w2_img, kW2ChunkBytes, &bar[3]);
+    }
+    // A: a tile's observations -> bf16, swizzled.  Every thread owns 8 of the tile's 2048 16-byte chunks (8 features each):
+    // all 64 loads are issued together into registers (one DRAM round trip), converted and stored later; rows and
+    // features beyond the data are zero.
+    float af[kTileM * (kInPad / 8) / kMlpThreads][8];
+    auto load_a = [&](int64_t row0, int nrows) {
+#pragma unroll
+        for (int it = 0; it < kTileM * (kInPad / 8) / kMlpThreads; ++it) {
+            const int i = tid + it * kMlpThreads, ar = i >> 4, k0 = (i & 15) * 8;
+            const float* src = obs + (row0 + ar) * in_dim + k0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) af[it][e] = (ar < nrows && k0 + e < in_dim) ? __ldcs(src + e) : 0.f;
+        }
+    };
+    auto store_a = [&]() {
+#pragma unroll
+        for (int it = 0; it < kTileM * (kInPad / 8) / kMlpThreads; ++it) {
+            const int i = tid + it * kMlpThreads, ar = i >> 4, k0 = (i & 15) * 8;
+            *reinterpret_cast<uint4*>(smem + kSmA + swz_offset(kTileM, ar, k0)) =
+                make_uint4(pack_bf16(af[it][0], af[it][1]), pack_bf16(af[it][2], af[it][3]), pack_bf16(af[it][4], af[it][5]), pack_bf16(af[it][6], af[it][7]));
+        }
+    };
+    int64_t step = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kTileM;
         const int nrows = rows - row0 < kTileM ? (int)(rows - row0) : kTileM;
-        // ---- A: the tile's observations (contiguous in memory) -> bf16, swizzled; padding rows / columns are zero
-        {
-            uint4* a4 = reinterpret_cast<uint4*>(smem + kSmA);
-            for (int i = tid; i < (kInPad / kAtomK) * kTileM * 8; i += kMlpThreads) a4[i] = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
-            const float* src = obs + row0 * in_dim;
-            const int total = nrows * in_dim;
-            for (int i = tid; i < total; i += kMlpThreads) {
-                const int r = i / in_dim, k = i - r * in_dim;
-                *reinterpret_cast<__nv_bfloat16*>(smem + kSmA + swz_offset(kTileM, r, k)) = __float2bfloat16_rn(__ldcs(src + i));
-            }
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-            // ---- this chunk's weight images: linear 16-byte copies (they are L2 residents: every CTA reads the same 300 KB)
-            {
-                const uint4* g1 = w1_img + (size_t)c * (kW1ChunkBytes / 16);
-                uint4* s1 = reinterpret_cast<uint4*>(smem + kSmW1);
-                for (int i = tid; i < kW1ChunkBytes / 16; i += kMlpThreads) s1[i] = __ldg(g1 + i);
-                const uint4* g2 = w2_img + (size_t)c * (kW2ChunkBytes / 16);
-                uint4* s2 = reinterpret_cast<uint4*>(smem + kSmW2);
-                for (int i = tid; i < kW2ChunkBytes / 16; i += kMlpThreads) s2[i] = __ldg(g2 + i);
-            }
+        if (tile == (int64_t)blockIdx.x) {  // the first tile: later ones are fetched and converted under the previous tile's last chunk
+            load_a(row0, nrows);
+            store_a();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
             __syncthreads();
-            // ---- layer 1: D1 = A . W1c^T
+        }
+        for (int c = 0; c < n_chunks; ++c, ++step) {
+            const int cn = c + 1 == n_chunks ? 0 : c + 1;  // the chunk of the next step
+            // ---- layer 1: D1 = A . W1c^T, as soon as W1c has landed
             if (tid == 0) {
+                mbar_wait(&bar[2], ph_w1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < kInPad / 16; ++k) {  // within a swizzle atom the start address advances by 32 bytes per K = 16
@@ -190,25 +221,32 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
                 }
                 umma_commit(&bar[0]);
             }
-            mbar_wait(&bar[0], ph0);
-            ph0 ^= 1;
+            ph_w1 ^= 1;
+            mbar_wait(&bar[0], ph_m1);  // D1 complete (and, the tensor pipe being in order, the previous step's layer 2: H is free)
+            ph_m1 ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // ---- hidden activations of my row: TMEM -> registers -> bias, ReLU, bf16 -> swizzled H
+            if (tid == 0 && step + 1 < n_steps) bulk_load(smem + kSmW1, w1_img + (size_t)cn * kW1ChunkBytes, kW1ChunkBytes, &bar[2]);
+            const bool fetch_next_a = c + 1 == n_chunks && tile + gridDim.x < n_tiles;  // this tile's last layer-1 MMAs have read A: it is free
+            if (fetch_next_a) {
+                const int64_t nrow0 = (tile + gridDim.x) * kTileM;
+                load_a(nrow0, rows - nrow0 < kTileM ? (int)(rows - nrow0) : kTileM);  // in flight under the epilogue below
+            }
+            // ---- hidden activations of my row, my 96 of the chunk's 192 columns: TMEM -> registers -> bias, ReLU, bf16 -> swizzled H
             {
-                const int r = tid;
                 const float* bc = b1 + c * kChunk;
 #pragma unroll 1
-                for (int j0 = 0; j0 < kChunk; j0 += 32) {
+                for (int j0 = half * (kChunk / 2); j0 < (half + 1) * (kChunk / 2); j0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(lane_base + kTmemD1 + j0, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {  // 8 hidden units = one 16-byte chunk of the swizzled row
+                        const float4 ba = __ldg(reinterpret_cast<const float4*>(bc + j0 + 8 * g)), bb = __ldg(reinterpret_cast<const float4*>(bc + j0 + 8 * g + 4));
+                        const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                         float h[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) h[e] = fmaxf(__uint_as_float(v[8 * g + e]) + __ldg(bc + j0 + 8 * g + e), 0.f);
-                        const int k = j0 + 8 * g;
-                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, k)) =
+                        for (int e = 0; e < 8; ++e) h[e] = fmaxf(__uint_as_float(v[8 * g + e]) + bias[e], 0.f);
+                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, j0 + 8 * g)) =
                             make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
                     }
                 }
@@ -218,6 +256,7 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
             __syncthreads();
             // ---- layer 2: D2 += H . W2c^T
             if (tid == 0) {
+                mbar_wait(&bar[3], ph_w2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < kChunk / 16; ++k) {
@@ -226,28 +265,34 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
                 }
                 umma_commit(&bar[1]);
             }
-            mbar_wait(&bar[1], ph1);  // H and the weight buffers are free again; after the last chunk D2 is complete
-            ph1 ^= 1;
+            ph_w2 ^= 1;
+            if (fetch_next_a) {  // the next tile's A, converted while layer 2 runs; made visible by the fence + barrier after the Q store
+                store_a();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            mbar_wait(&bar[1], ph_m2);  // the W2 buffer is free again; after the last chunk D2 is complete
+            ph_m2 ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0 && step + 1 < n_steps) bulk_load(smem + kSmW2, w2_img + (size_t)cn * kW2ChunkBytes, kW2ChunkBytes, &bar[3]);
         }
-        // ---- Q = D2 + b2, my row
+        // ---- Q = D2 + b2: my row, my half of the columns (80 + 64)
         {
-            const int r = tid;
-            float* qr = q + (row0 + r) * out_dim;
+            float* qr = q + (row0 + r) * q_row_stride;
+            const int jbeg = half ? 80 : 0, jend = half ? kOutPad : 80;
 #pragma unroll 1
-            for (int j0 = 0; j0 < kOutPad; j0 += 16) {
+            for (int j0 = jbeg; j0 < jend; j0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(lane_base + kTmemD2 + j0, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (r < nrows) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (j0 + e < out_dim) qr[j0 + e] = __uint_as_float(v[e]) + __ldg(b2 + j0 + e);
+                        if (j0 + e < out_dim) qr[(int64_t)(j0 + e) * q_col_stride] = __uint_as_float(v[e]) + __ldg(b2 + j0 + e);
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // the next tile's first MMAs overwrite D1 / D2, its loads overwrite A
+        __syncthreads();  // the next tile's first MMAs overwrite D1 / D2, its conversion overwrites A
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
@@ -255,7 +300,7 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
 }  // namespace
 
 cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const float* b1, const void* w2_img, const float* b2,
-                              int n_chunks, int out_dim, float* q, int sm_count, cudaStream_t stream)
+                              int n_chunks, int out_dim, float* q, int transposed, int sm_count, cudaStream_t stream)
 {
     if (rows <= 0) return cudaSuccess;
     static bool attr_set = false;
@@ -266,8 +311,9 @@ cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const 
     }
     const int64_t tiles = (rows + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
-    evg_policy_mlp_kernel<<<grid, kMlpThreads, kSmBytes, stream>>>(obs, rows, in_dim, reinterpret_cast<const uint4*>(w1_img), b1,
-                                                                   reinterpret_cast<const uint4*>(w2_img), b2, n_chunks, out_dim, q);
+    evg_policy_mlp_kernel<<<grid, kMlpThreads, kSmBytes, stream>>>(obs, rows, in_dim, reinterpret_cast<const unsigned char*>(w1_img), b1,
+                                                                   reinterpret_cast<const unsigned char*>(w2_img), b2, n_chunks, out_dim, q,
+                                                                   transposed ? 1 : out_dim, transposed ? rows : 1);
     return cudaGetLastError();
 }
 

@@ -87,16 +87,29 @@ class FusedDQN:
         self._b1 = torch.from_numpy(b1p).to(dev)
         self._b2 = torch.from_numpy(b2).to(dev)
         self.q = torch.empty((env.num_envs, 2, self.out_dim), dtype=torch.float32, device=dev)
+        self.qt = torch.empty((self.out_dim, env.num_envs * 2), dtype=torch.float32, device=dev)
 
-    def forward(self, obs=None):
-        """Q-values float32 [N, 2, out] for `obs` (default: the environment's own observation tensor)."""
+    def _run(self, obs, out, transposed):
         env = self.env
         obs = env.obs if obs is None else obs
         _capi.check(env._lib.evg_policy_mlp(env._h, C.c_void_p(obs.data_ptr()), env.num_envs * 2, C.c_void_p(self._w1.data_ptr()),
                                             C.c_void_p(self._b1.data_ptr()), C.c_void_p(self._w2.data_ptr()), C.c_void_p(self._b2.data_ptr()),
-                                            self.hidden, self.out_dim, C.c_void_p(self.q.data_ptr()), env._stream()))
-        return self.q
+                                            self.hidden, self.out_dim, C.c_void_p(out.data_ptr()), int(transposed), env._stream()))
+        return out
+
+    def forward(self, obs=None):
+        """Q-values float32 [N, 2, out] for `obs` (default: the environment's own observation tensor)."""
+        return self._run(obs, self.q, False)
+
+    def forward_t(self, obs=None):
+        """The same Q-values transposed, float32 [out, N * 2]: what the decode reads coalesced."""
+        return self._run(obs, self.qt, True)
 
     def __call__(self):
         """Action rows int8 [N, 2, 7, 2] for both players: forward, then DQNAgent.filter_actions on the device."""
-        return self.env.decode_dqn(self.forward())
+        env = self.env
+        qt = self.forward_t()
+        assert self.out_dim % _capi.NUM_GROUPS == 0
+        _capi.check(env._lib.evg_decode_dqn_layout(env._h, C.c_void_p(qt.data_ptr()), self.out_dim // _capi.NUM_GROUPS, -1, 1,
+                                                   C.c_void_p(env._actions.data_ptr()), env._stream()))
+        return env._actions

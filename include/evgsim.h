@@ -290,6 +290,8 @@ int evg_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_action
  *   evg_decode_indices: int64 flat indices [..][7] -> rows (idx / div, idx % mod); PPOAgent.get_action uses
  *                       div 12, mod 11 (agents/PPO/PPOAgent.py:122-127), DQN's replay encoding div 11, mod 11. */
 int evg_decode_dqn(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int8_t* d_actions, void* stream);
+/* the same with d_q optionally transposed: [12 * num_cols][rows], rows = n_envs * (player < 0 ? 2 : 1) */
+int evg_decode_dqn_layout(EvgSim* sim, const float* d_q, int32_t num_cols, int32_t player, int32_t q_transposed, int8_t* d_actions, void* stream);
 int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t mod, int32_t player, int8_t* d_actions,
                        void* stream);
 
@@ -303,12 +305,13 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
  *     d_w2_img + c * (EVG_MLP_CHUNK / 64) * EVG_MLP_OUT_PAD * 128 bytes: W2[o][c*CHUNK + k], o < OUT_PAD, k < CHUNK
  * element (row r, column k) of a [R x K] block at byte (k/64)*R*128 + r*128 + ((((k%64)/8) ^ (r%8)) * 16) + (k%8)*2, zero
  * padded; d_b1 has ceil(hidden / CHUNK) * CHUNK floats (zero padded), d_b2 out_dim floats.  evgsim.policy.pack_mlp builds
- * them from a torch module.  Decode d_q with evg_decode_dqn. */
+ * them from a torch module.  q_transposed != 0 writes d_q as [out_dim][rows] instead (each output's values for all rows
+ * contiguous): the layout evg_decode_dqn_layout reads coalesced. */
 #define EVG_MLP_IN_PAD 128
 #define EVG_MLP_CHUNK 192
 #define EVG_MLP_OUT_PAD 144
 int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const float* d_b1, const void* d_w2_img,
-                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, void* stream);
+                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, int32_t q_transposed, void* stream);
 
 /* Reward shaping of the reference's training scripts (utils/reward_shaping.py:17-56) on the step's outputs:
  * d_out float32 [n_envs][2].  turnNum (steps played before this one) is read from the observation's turn

@@ -36,6 +36,7 @@ def test_fused_forward_matches_torch(evg, cfg, n, hidden, out):
     net = make_net(torch, n, hidden, out, scale=3.0)
     fused = policy.FusedDQN(env, net)
     q = fused.forward().cpu().numpy().reshape(2 * n, out)
+    assert np.array_equal(fused.forward_t().cpu().numpy(), q.T)  # the transposed output holds the same values
     obs = env.obs.view(-1, 105)
     w = [t.detach().float().numpy() for t in (net[0].weight, net[0].bias, net[2].weight, net[2].bias)]
     want = policy.reference_forward(obs.cpu().numpy(), *w)
@@ -59,7 +60,7 @@ def test_fused_policy_in_the_loop_equals_decode_of_its_own_q(evg, cfg):
     fused = policy.FusedDQN(env, make_net(torch, 1))
     for t in range(40):
         acts = fused()
-        q = fused.q.cpu().numpy()
+        q = fused.qt.cpu().numpy().T.reshape(n, 2, 132)
         a = acts.cpu().numpy()
         for i in range(0, n, 17):
             for p in range(2):

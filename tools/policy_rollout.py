@@ -76,6 +76,8 @@ def main():
     ap.add_argument("--policy", default="dqn", choices=["dqn", "ppo", "rppo"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--graph", action="store_true", help="replay the turn (forward, decode, step) from a CUDA graph")
+    ap.add_argument("--fused", action="store_true",
+                    help="dqn only: the forward runs in libevgsim's fused tcgen05 kernel (evg_policy_mlp, bf16 operands) instead of torch")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -91,8 +93,14 @@ def main():
     env.reset()
     hidden = torch.zeros((1, 2 * E, 128), dtype=dtype, device=env.device) if args.policy == "rppo" else None
 
+    fused = None
+    if args.fused:
+        assert args.policy == "dqn", "--fused is the DQN network's kernel"
+        from evgsim import policy as evp
+        fused = evp.FusedDQN(env, net.float())
+
     def turn():
-        env.step(policy_actions(env, net, args.policy, dtype, hidden))
+        env.step(fused() if fused is not None else policy_actions(env, net, args.policy, dtype, hidden))
         if hidden is not None:  # a finished match starts over with a fresh hidden state
             hidden.mul_((1 - env.done).to(dtype).repeat_interleave(2).view(1, -1, 1))
 
@@ -125,7 +133,8 @@ def main():
     stats = evgsim.gather_episode_stats(env.episode_stats(), device=env.device) if world > 1 else env.episode_stats()
     if rank == 0:
         sec = float(ms.item()) / 1e3
-        print(json.dumps({"workload": "policy-in-the-loop self-play (BASELINE.json configs[3])", "policy": args.policy, "dtype": args.dtype, "cuda_graph": bool(args.graph),
+        print(json.dumps({"workload": "policy-in-the-loop self-play (BASELINE.json configs[3])", "policy": args.policy, "dtype": "bf16 operands, fp32 accumulate (evg_policy_mlp)" if args.fused else args.dtype, "fused_forward": bool(args.fused),
+                          "cuda_graph": bool(args.graph),
                           "n_gpus": world, "envs_per_gpu": E, "turns": args.turns, "env_turns_per_s": E * world * args.turns / sec,
                           "ms_per_turn": sec * 1e3 / args.turns, "episodes": stats["episodes"], "wins": stats["wins"], "ties": stats["ties"]}))
     if world > 1:
