@@ -9,12 +9,13 @@ here=$(dirname $(realpath $0)); root=$(dirname $here); out=$root/profiles
 src=$root/everglades-ai-wargame_b200/csrc/evg_step_tpm.cu
 k=${KERNEL:-evg_step_tpm_kernelILi11ELi12EhLi94ELb0ELi128ELb0E}
 matches=${MATCHES:-262144}
+phase=${PHASE:-staggered}
 d=$(mktemp -d); cd $d
 ncu -i $rep --page source --csv > sass.csv 2>/dev/null
 ncu -i $rep --page raw --csv > raw.csv 2>/dev/null
 cuobjdump -xelf all $lib > /dev/null
 nvdisasm -g -c evg_step_tpm.sm_100a.cubin > k.sass 2>/dev/null
-python - "$out/${tag}_raw.csv" "$out/step_kernel_traffic.json" "$tag" "$matches" <<'PY'
+python - "$out/${tag}_raw.csv" "$out/step_kernel_traffic.json" "$tag" "$matches" "$phase" <<'PY'
 import csv, json, sys
 rows = list(csv.reader(open('raw.csv')))
 d = dict(zip(rows[0], zip(rows[1], rows[2])))
@@ -38,10 +39,18 @@ with open(sys.argv[1], 'w') as f:
 unit = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}
 rd = float(d['dram__bytes_read.sum'][1]) * unit[d['dram__bytes_read.sum'][0]]
 wr = float(d['dram__bytes_write.sum'][1]) * unit[d['dram__bytes_write.sum'][0]]
-m = int(sys.argv[4])
-json.dump({"kernel": d['Kernel Name'][1], "source": "profiles/%s_raw.csv (ncu --set full --clock-control none, %d matches, launch at game turn 76 of random-vs-random: the combat-heaviest part of an episode)" % (sys.argv[3], m),
-           "dram_bytes_read_per_launch": rd, "dram_bytes_write_per_launch": wr, "matches_per_launch": m,
-           "dram_bytes_per_env_turn": (rd + wr) / m, "algorithmic_bytes_per_env_turn": 1676}, open(sys.argv[2], 'w'), indent=1)
+m, phase = int(sys.argv[4]), sys.argv[5]
+# one entry per (batch size, phase mix): bench.py reports roofline.traffic only from a capture of ITS batch size and phase
+try:
+    doc = json.load(open(sys.argv[2]))
+    caps = [c for c in doc.get("captures", []) if not (int(c["envs"]) == m and c.get("phase") == phase)]
+except Exception:
+    caps = []
+caps.append({"envs": m, "phase": phase, "kernel": d['Kernel Name'][1], "dram_bytes_read_per_launch": rd, "dram_bytes_write_per_launch": wr,
+             "dram_bytes_per_launch": rd + wr, "dram_bytes_per_env_turn": (rd + wr) / m, "gpu_time_us": float(d['gpu__time_duration.sum'][1]),
+             "source": "profiles/%s_raw.csv (ncu --set full --clock-control none, one launch of a settled `bench.py --phase %s --envs-per-gpu %d` run)" % (sys.argv[3], phase, m)})
+json.dump({"what": "DRAM bytes of one step-kernel launch (dram__bytes_read.sum + dram__bytes_write.sum), per batch size and phase mix",
+           "captures": sorted(caps, key=lambda c: (c["envs"], c["phase"]))}, open(sys.argv[2], 'w'), indent=1)
 PY
 python $here/ncu_phases.py sass.csv k.sass $k $src > $out/${tag}_phases.txt
 python $here/ncu_lines.py sass.csv k.sass $k $src 2>&1 | head -80 | cut -c1-170 > $out/${tag}_lines.txt

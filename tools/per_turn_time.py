@@ -21,4 +21,5 @@ for t in range(150):
     ev.append((e0, e1))
 torch.cuda.synchronize()
 ms = [a.elapsed_time(b) for a, b in ev]
-print(json.dumps({"matches": n, "mean_ms": sum(ms) / len(ms), "per_turn_ms": [round(x, 4) for x in ms]}))
+print(json.dumps({"matches": n, "mean_ms": sum(ms) / len(ms), "per_turn_ms": [round(x, 4) for x in ms],
+                  "fought_unit_slots_per_env_turn": env.episode_stats()["fought_unit_slots"] / (150.0 * n)}))
