@@ -12,10 +12,6 @@
 
 #include "evg_internal.h"
 
-#ifndef EVG_TPM_SMALL_MAX_DEFAULT
-#define EVG_TPM_SMALL_MAX_DEFAULT 65536  // matches up to which the one-warp-per-CTA instantiation is used (env EVG_TPM_SMALL_MAX)
-#endif
-
 namespace {
 
 thread_local std::string g_last_error;
@@ -54,6 +50,7 @@ struct EvgSim {
     EvgLayout layout;
     bool use_tpm;     // the thread-per-match step kernel, or the warp-per-match one (small batches, EVG_STEP_KERNEL=warp)
     const uint4* tables_dev;  // Tables in device memory (inside bind slot EVG_BIND_TABLES)
+    const float* oconst_dev;  // the constant observation entries behind it
     // evg_step_host's chunk pipeline: two streams of the library's own, created on first use
     cudaStream_t host_stream[2] = {nullptr, nullptr};
     cudaEvent_t host_start = nullptr, host_done[2] = {nullptr, nullptr};
@@ -328,16 +325,31 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     // default: a thread per match, except for small batches, where a warp per match spreads the few matches over all
     // SMs (measured: 4,096 matches 2.0e8 vs 1.2e8 env-turns/s; break-even near 16k, profiles/README.md)
     s->use_tpm = which ? strcmp(which, "warp") != 0 : n_envs >= 12288;
-    // mid-size batches: one warp per CTA spreads the warps over all SMs (measured: +9 % at 65,536 matches, +5 % at
-    // 32,768, slower from 98,304 on where the 128-thread CTAs' shared instruction stream wins; profiles/README.md)
+    // Thread-per-match kernel: 128-thread CTAs, except where a batch needs a second round of them although all of it fits
+    // one wave of one-warp CTAs (the LITE instantiation keeps no tables in shared memory: 14 CTAs per SM, 66,304 matches
+    // resident on 148 SMs).  Measured step times, lite / 128-thread (profiles/README.md): 32,768 matches 32 / 30 us,
+    // 65,536 46 / 55 us, 98,304 70 / 65 us, 262,144 178 / 144 us.  EVG_TPM_SMALL_MAX=<matches> forces the one-warp CTAs up to
+    // that batch size (0: never).
     {
-        const char* small = getenv("EVG_TPM_SMALL_MAX");
-        const int64_t small_max = small ? atoll(small) : EVG_TPM_SMALL_MAX_DEFAULT;
-        s->tpm_threads = evg::tpm_has_small(t) && n_envs <= small_max ? evg::kTpmSmallThreads : evg::kTpmThreads;
+        int per_sm128 = 0, per_sm32 = 0;
+        size_t smem128 = 0, smem32 = 0;
+        if ((e = evg::tpm_prepare(t, evg::kTpmThreads, &smem128, &per_sm128)) != cudaSuccess || per_sm128 < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
+        s->tpm_threads = evg::kTpmThreads;
+        s->tpm_smem = smem128;
+        s->tpm_grid = prop.multiProcessorCount * per_sm128;
+        if (evg::tpm_has_small(t)) {
+            if ((e = evg::tpm_prepare(t, evg::kTpmSmallThreads, &smem32, &per_sm32)) != cudaSuccess || per_sm32 < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup (one-warp CTAs)"); }
+            const int64_t nb128 = (n_envs + evg::kTpmThreads - 1) / evg::kTpmThreads;
+            const int64_t lite_capacity = (int64_t)prop.multiProcessorCount * per_sm32 * evg::kTpmSmallThreads;
+            bool lite = nb128 > s->tpm_grid && n_envs <= lite_capacity;
+            if (const char* small = getenv("EVG_TPM_SMALL_MAX")) lite = n_envs <= atoll(small);
+            if (lite) {
+                s->tpm_threads = evg::kTpmSmallThreads;
+                s->tpm_smem = smem32;
+                s->tpm_grid = prop.multiProcessorCount * per_sm32;
+            }
+        }
     }
-    int tpm_per_sm = 0;
-    if ((e = evg::tpm_prepare(t, s->tpm_threads, &s->tpm_smem, &tpm_per_sm)) != cudaSuccess || tpm_per_sm < 1) { delete s; return cuda_fail(e, "thread-per-match kernel setup"); }
-    s->tpm_grid = prop.multiProcessorCount * tpm_per_sm;
     s->sm_count = prop.multiProcessorCount;
     if ((e = evg::set_step_smem(s->smem)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)"); }
     int per_sm = 0;
@@ -357,7 +369,9 @@ int evg_create(const EvgConfig* cfg, int64_t n_envs, uint64_t seed, int64_t env_
     L.stats_bytes = (evg::ST_COUNT + evg::kSchedSlots + 1) * 8;  // + the step kernel's batch hand-out counters + evg_import_state's error counter
     L.agents_bytes = n_envs * 16;
     // loss table, then reciprocals, then the Tables struct itself (the step kernel stages it from here)
-    L.tables_bytes = round_up((int)((int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8), 16) + round_up((int)sizeof(evg::Tables), 16);
+    // ... and the constant observation entries as floats
+    L.tables_bytes = round_up((int)((int64_t)cfg->n_unit_types * (cfg->n_nodes + 1) * 3 * (evg::kLossD + 1) * 8), 16) + round_up((int)sizeof(evg::Tables), 16) +
+                     round_up(evg::oconst_bytes(cfg->n_nodes), 16);
     *out = s;
     return EVG_OK;
 }
@@ -424,6 +438,29 @@ int evg_bind(EvgSim* sim, void* const* device_ptrs, int32_t n_ptrs)
         e = cudaMemcpy(tdev, &sim->tables, sizeof(evg::Tables), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cuda_fail(e, "upload of the static tables");
         sim->tables_dev = (const uint4*)tdev;
+        // the observation entries that never change, as the floats the step kernels copy into every observation:
+        // the nodes' 'DEFENSE' / 'OBSERVE' flags in each viewer's numbering (server.py:437-443) and the groups' unit
+        // types (server.py:476); everything else 0
+        {
+            const evg::Tables& t = sim->tables;
+            const int OL = t.obs_len, n = t.n_nodes, oc_floats = (2 * OL + 3) & ~3;
+            std::vector<float> oc(evg::oconst_bytes(n) / 4, 0.f);
+            for (int p = 0; p < 2; ++p) {
+                for (int k = 0; k < n; ++k) {
+                    const int x = p ? t.p1_map[k + 1] : k + 1;
+                    const float fd = (float)(t.node_flags[x] & 1u), fo = (float)((t.node_flags[x] >> 1) & 1u);
+                    oc[p * OL + 1 + 4 * k] = fd;
+                    oc[p * OL + 1 + 4 * k + 1] = fo;
+                    oc[oc_floats + 2 * (p * n + k)] = fd;
+                    oc[oc_floats + 2 * (p * n + k) + 1] = fo;
+                }
+                for (int g = 0; g < EVG_NUM_GROUPS; ++g) oc[p * OL + 1 + 4 * n + 5 * g + 1] = (float)t.g_type[p * EVG_NUM_GROUPS + g];
+            }
+            char* odev = tdev + round_up((int)sizeof(evg::Tables), 16);
+            e = cudaMemcpy(odev, oc.data(), oc.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return cuda_fail(e, "upload of the constant observation entries");
+            sim->oconst_dev = (const float*)odev;
+        }
     }
     sim->is_bound = true;
     return EVG_OK;
@@ -506,6 +543,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
     a.tables_dev = sim->tables_dev;
+    a.oconst_dev = sim->oconst_dev;
     a.env_first = 0;
     if (count >= 0) {
         const evg::Tables& t = sim->tables;
@@ -600,6 +638,7 @@ int evg_rollout(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int32_t n_turns
     a.scores = d_scores;
     a.n_envs = sim->n_envs;
     a.tables_dev = sim->tables_dev;
+    a.oconst_dev = sim->oconst_dev;
     cudaError_t e = evg::launch_rollout(sim->tables, a, n_turns, sim->grid, sim->smem, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_rollout_kernel launch");
     sim->launches += 1;

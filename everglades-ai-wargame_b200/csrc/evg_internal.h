@@ -96,6 +96,9 @@ constexpr int kTpmSmallThreads = 32;  // the one-warp-per-CTA instantiation for 
 #ifndef EVG_TPM_MIN_CTAS
 #define EVG_TPM_MIN_CTAS 3
 #endif
+#ifndef EVG_TPM_LITE_MIN_CTAS
+#define EVG_TPM_LITE_MIN_CTAS 14  // resident one-warp CTAs per SM the LITE instantiation is compiled for (register cap 144)
+#endif
 #ifndef EVG_TPM_SYNC
 #define EVG_TPM_SYNC 1  // CTA barriers at the phase boundaries named by EVG_TPM_SYNC_MASK (0: free-running warps)
 #endif
@@ -125,12 +128,21 @@ struct StepArgs {
     int32_t agent[2];      // EVG_AGENT_*: where each player's action rows come from
     int8_t* actions_out;   // optional: rows generated by scripted agents are also written here
     const uint4* tables_dev;  // the Tables struct in device memory (bind slot EVG_BIND_TABLES): staged with coalesced loads
+    const float* oconst_dev;  // behind it: the constant observation entries as floats (oconst_bytes(n_nodes), filled by evg_bind)
     int64_t env_first;        // thread-per-match kernel: this launch covers matches [env_first, env_first + n_envs) of the
                               // simulator (all pointers above are already offset); 0 for a whole-batch launch
     unsigned* sched;          // thread-per-match kernel: {batches handed out after the first wave, CTAs finished}, zero between launches
     uint2* agent_state;       // per (match, player) state of the observation-driven scripted agents (bind slot EVG_BIND_AGENTS)
     int32_t obs_fmt;          // EVG_OBS_F32: `obs` is float32[n][2][obs_len]; EVG_OBS_WIRE: packed rows of wire_bytes(n_nodes)
 };
+
+// bytes of the constant observation entries a step kernel keeps at hand: 2 * obs_len floats (padded to 16 bytes), then
+// per [player][viewer slot] the node's two flags as a float2
+__host__ __device__ inline int oconst_bytes(int n_nodes)
+{
+    const int ol = 1 + 4 * n_nodes + 5 * EVG_NUM_GROUPS;
+    return ((2 * ol + 3) & ~3) * 4 + ((2 * n_nodes * 8 + 15) & ~15);
+}
 
 // bytes of one match's wire row (include/evgsim.h, EVG_OBS_WIRE)
 __host__ __device__ inline int wire_bytes(int n_nodes) { return (EVG_WIRE_NODE0 + 4 * n_nodes + 3 * kGroupLanes + 8 + 15) / 16 * 16; }

@@ -146,7 +146,7 @@ __device__ __noinline__ void load_rows_direct(const StepArgs& A, uint32_t* wrow,
 // WIRE: the observation output is the packed wire row of include/evgsim.h (EVG_OBS_WIRE: 128 bytes per match on DemoMap,
 // both players' observations + rewards + done in one cache line) instead of float32[2][obs_len] (840 bytes)
 template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS, int THREADS, bool WIRE = false>
-__global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_CTAS : 1) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
+__global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_CTAS : EVG_TPM_LITE_MIN_CTAS) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -158,7 +158,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     // Software pipeline (compile-time map only: 16 chunks of 16 bytes per record): the NEXT batch's records and
     // action rows are requested into registers before this batch's observation phase, so their DRAM latency is
     // hidden behind a fifth of a batch's work instead of being exposed at the top of every batch
-    constexpr bool PIPE = NODES != 0 && EVG_TPM_PIPE != 0;
+    // LITE = the one-warp-per-CTA instantiation for mid-size batches (a few thousand warps: one or two waves).  There the
+    // number of RESIDENT warps decides, so everything a CTA would hold once is left out of shared memory — the static
+    // tables and the constant observation entries are read from device memory through L1 instead (15.4 KB per CTA instead
+    // of 19.7: 14 CTAs per SM instead of 11, 65,536 matches in ONE wave) — and the next-batch register pipeline, which a
+    // CTA that runs one or two batches has no use for, gives its 71 registers back.
+    constexpr bool LITE = THREADS == kTpmSmallThreads;
+    constexpr bool PIPE = NODES != 0 && EVG_TPM_PIPE != 0 && !LITE;
     uint4 nxt[16];
     uint32_t nxa[7];
     bool have = false;
@@ -181,60 +187,53 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     static_assert(EVG_TPM_SYNC && ((EVG_TPM_SYNC_MASK >> 3) & 1), "the batch hand-over uses the barrier before the observation phase");
     // (the two hand-over slots live in the CTA's copy of the tables: static shared memory would come off the opt-in limit)
     uint32_t first_draw = 0;
-    if (threadIdx.x == 0) first_draw = gridDim.x + atomicAdd(&A.sched[0], 1u);
+    if (!LITE && threadIdx.x == 0) first_draw = gridDim.x + atomicAdd(&A.sched[0], 1u);
     // ---- stage the static tables once per CTA
-    {   // from device memory with coalesced 16-byte loads (per-lane addresses into the parameter bank would be serialised)
+    if (!LITE) {   // from device memory with coalesced 16-byte loads (per-lane addresses into the parameter bank would be serialised)
         static_assert(sizeof(Tables) % 16 == 0, "Tables is copied in 16-byte pieces");
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 16); i += blockDim.x) dst[i] = __ldg(A.tables_dev + i);
     }
-    const Tables& S = *reinterpret_cast<const Tables*>(smem);
-    __syncthreads();
-    volatile uint32_t* sched = reinterpret_cast<Tables*>(smem)->cta_sched;
-    if (threadIdx.x == 0) {
-        sched[0] = first_draw;
-        // a sub-range launch (evg_step_host's chunks): global match ids start further on
-        reinterpret_cast<Tables*>(smem)->env_base += (uint32_t)A.env_first;
-    }
-    int par = 1;
-
+    const Tables* tables_ptr;  // (if constexpr: a pointer that could be either would be dereferenced with generic loads)
+    if constexpr (LITE) tables_ptr = reinterpret_cast<const Tables*>(A.tables_dev);
+    else tables_ptr = reinterpret_cast<const Tables*>(smem);
+    const Tables& S = *tables_ptr;
+    if (!LITE) __syncthreads();  // the run-time-sized instantiations read their sizes from the staged tables
     const Geo<NODES> G(S);
     const int n_nodes = G.n_nodes(), nn = G.nn(), RW = G.rw(), OL = G.obs_len();
+    // the observation entries that never change (a third of them: the nodes' DEFENSE/OBSERVE flags in each viewer's
+    // numbering and the groups' unit types) were converted to float once, by evg_bind (A.oconst_dev: 2*OL floats, then per
+    // [player][viewer slot] the node's two flags); a CTA keeps a copy in shared memory, LITE reads them in place
+    const int oc_floats = (2 * OL + 3) & ~3;
+    const int oc_bytes = oc_floats * 4 + ((2 * n_nodes * 8 + 15) & ~15);
+    const float* oconst;
+    if constexpr (LITE) oconst = A.oconst_dev;
+    else oconst = reinterpret_cast<const float*>(smem + T.sm_tables_bytes);
+    const float2* ocpair = reinterpret_cast<const float2*>(oconst + oc_floats);
+    volatile uint32_t* sched = reinterpret_cast<Tables*>(smem)->cta_sched;
+    if (!LITE) {
+        uint4* dst = reinterpret_cast<uint4*>(smem + T.sm_tables_bytes);
+        for (int i = threadIdx.x; i < oc_bytes / 16; i += blockDim.x) dst[i] = __ldg(reinterpret_cast<const uint4*>(A.oconst_dev) + i);
+        if (threadIdx.x == 0) {
+            sched[0] = first_draw;
+            // a sub-range launch (evg_step_host's chunks) covers global match ids that start further on
+            reinterpret_cast<Tables*>(smem)->env_base += (uint32_t)A.env_first;
+        }
+        __syncthreads();
+    }
+    int par = 1;
+    // (re-read from the tables where it is used: one more register held across the batch loop costs the 128-thread kernel 2 %)
+    auto env_base_of = [&]() -> uint32_t { return LITE ? S.env_base + (uint32_t)A.env_first : S.env_base; };
     // player 1's node numbering (server.py:89): two registers of nibbles on the compile-time map, the byte table otherwise
     const uint64_t p1n = S.p1_nib;
     auto p1map = [&](uint32_t i) -> uint32_t { return NODES ? (uint32_t)(p1n >> (4 * i)) & 15u : (uint32_t)S.p1_map[i]; };
-    // the observation entries that never change (a third of them: the nodes' DEFENSE/OBSERVE flags in each viewer's
-    // numbering and the groups' unit types) are converted once per CTA; packing copies them from here
-    float* oconst = reinterpret_cast<float*>(smem + T.sm_tables_bytes);
-    const int oc_floats = (2 * OL + 3) & ~3;
-    float2* ocpair = reinterpret_cast<float2*>(oconst + oc_floats);  // [player][viewer slot]: the node's two flags
-    const int oc_bytes = oc_floats * 4 + ((2 * n_nodes * 8 + 15) & ~15);
-    for (int i = threadIdx.x; i < 2 * n_nodes; i += blockDim.x) {
-        const int p = i >= n_nodes ? 1 : 0, k = i - p * n_nodes;
-        const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
-        ocpair[i] = make_float2((float)(S.node_flags[x] & 1u), (float)((S.node_flags[x] >> 1) & 1u));
-    }
-    for (int f = threadIdx.x; f < 2 * OL; f += blockDim.x) {
-        const int p = f >= OL ? 1 : 0, i = f - p * OL;
-        float v = 0.f;
-        if (i >= 1 && i < 1 + 4 * n_nodes) {
-            const int k = (i - 1) >> 2, j = (i - 1) & 3;
-            const int x = p ? (int)S.p1_map[k + 1] : k + 1;  // server.py:437-439
-            if (j < 2) v = (float)((S.node_flags[x] >> j) & 1u);
-        } else if (i >= 1 + 4 * n_nodes) {
-            const int q = i - 1 - 4 * n_nodes, g = q / 5;
-            if (q - 5 * g == 1) v = (float)S.g_type[p * EVG_NUM_GROUPS + g];
-        }
-        oconst[f] = v;
-    }
-    __syncthreads();
-    int64_t next_batch = sched[0];
+    int64_t next_batch = LITE ? (int64_t)blockIdx.x + gridDim.x : (int64_t)sched[0];
     const int P = PITCH ? PITCH : T.tpm_pitch;
     const int RWU = (kRecNode0 + n_nodes + 1) & ~1;  // record words a row keeps (the padding stays in global memory)
     // per warp: 32 rows (record + observation staging window), the node words of its 32 matches stored
     // word-major ([word][lane]: a thread's own accesses always hit bank `lane`, whatever the index), the pool
     const int WS = 32 * P + 64 * nn + T.tpm_pool_words;
-    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + T.sm_tables_bytes + oc_bytes) + (size_t)warp * WS;  // the warp's 32 rows
+    uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + (LITE ? 0 : T.sm_tables_bytes + oc_bytes)) + (size_t)warp * WS;  // the warp's 32 rows
     uint32_t* R = wrow + (size_t)lane * P;  // my record
     uint32_t* wx = wrow + 32 * P;           // node words of the warp's matches: word i of match m at wx[32 * i + m]
     uint32_t* X = wx + lane;                // mine: X[32 * i]
@@ -292,11 +291,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 for (int pl = 0; pl < 2; ++pl) {
                     uint32_t* pr = rows + pl * EVG_MAX_ACTIONS;
                     if (A.agent[pl] == EVG_AGENT_RANDOM) {
-                        agent_random_rows(S.env_base + (uint32_t)env, turn, episode, pl, n_nodes, S.seed_lo, S.seed_hi, pr);
+                        agent_random_rows(env_base_of() + (uint32_t)env, turn, episode, pl, n_nodes, S.seed_lo, S.seed_hi, pr);
                     } else if (A.agent[pl] != EVG_AGENT_EXTERNAL) {
                         uint2 st = A.agent_state[env * 2 + pl];
                         if (A.agent[pl] == EVG_AGENT_BASE_RUSH) agent_base_rush_rows(S, w0_of, st, pl, pr);
-                        else agent_swarm_rows(S, w0_of, st, S.env_base + (uint32_t)env, turn, episode, pl, pr);
+                        else agent_swarm_rows(S, w0_of, st, env_base_of() + (uint32_t)env, turn, episode, pl, pr);
                         A.agent_state[env * 2 + pl] = st;
                     }
                 }
@@ -350,6 +349,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         uint32_t fm = 0;          // my match's fighting groups (bit L = side * 12 + gid)
         uint32_t xm = 0;          // those of them whose second draw block is a work item
         uint32_t b0 = 0, b1 = 0;  // histogram entries per side = alive units of the fighting groups
+        uint32_t my_slots = 0;    // unit slots of my match's fighting groups (ST_FOUGHT)
         if (valid) {
             for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
             {
@@ -398,10 +398,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                     slots += size;
                 }
                 // ST_FOUGHT: unit slots whose health this turn's combat reads; gathered per CTA in a spare table word
-                atomicAdd(&reinterpret_cast<Tables*>(smem)->cta_fought, slots);
+                // (LITE has no shared-memory tables: summed over the warp below)
+                if (LITE) my_slots = slots;
+                else atomicAdd(&reinterpret_cast<Tables*>(smem)->cta_fought, slots);
             }
         }
         __syncwarp();  // rows (actions applied, node words) are read by other lanes from here on
+        if (LITE) {
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, my_slots);
+            if (lane == 0 && tot) atomicAdd(&A.stats[ST_FOUGHT], (unsigned long long)tot);
+        }
         EVG_PHASE_SYNC(1);
         // the warp's work list = concatenation of the matches' fighting groups (then their second draw blocks); a
         // round takes whole matches (a match has <= 32 items), so draws and apply of one match stay in one round and the
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 const uint32_t turn_m = te.x + 1u, ep_m = te.y;
                 for (uint32_t b = jb; 8u * (b - jb) < nd; ++b) {
                     uint32_t r[4];
-                    philox4x32_10(S.env_base + (uint32_t)(warp_env0 + m), turn_m,
+                    philox4x32_10(env_base_of() + (uint32_t)(warp_env0 + m), turn_m,
                                   (uint32_t)x | (uint32_t)side << 8 | (uint32_t)gg << 16 | b << 24, ep_m << 8, S.seed_lo, S.seed_hi, r);
 #pragma unroll
                     for (uint32_t k = 0; k < 8; ++k)
@@ -656,9 +662,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
 #if EVG_TPM_REQUEST_AT == 0
     if (PIPE) have = request(next_batch);  // in flight across the barrier
 #endif
-    if (threadIdx.x == 0) sched[par] = gridDim.x + atomicAdd(&A.sched[0], 1u);  // the batch after next
+    if (!LITE && threadIdx.x == 0) sched[par] = gridDim.x + atomicAdd(&A.sched[0], 1u);  // the batch after next
     EVG_PHASE_SYNC(3);
-    const int64_t after_next = sched[par];
+    const int64_t after_next = LITE ? next_batch + gridDim.x : (int64_t)sched[par];
     par ^= 1;
 
     // ---- observations: board_state (server.py:382-455) + player_state (:457-501) + concat (env.py:158-171).
@@ -795,6 +801,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     batch = next_batch;
     next_batch = after_next;
     }  // batch loop
+    if (LITE) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         if (S.cta_fought) atomicAdd(&A.stats[ST_FOUGHT], (unsigned long long)S.cta_fought);
@@ -824,7 +831,8 @@ bool tpm_has_small(const Tables& t) { return pick(t) == V_FAST; }
 
 static size_t tpm_smem_bytes(const Tables& t, int threads)
 {
-    size_t smem = (size_t)t.sm_tables_bytes + (size_t)(((2 * t.obs_len + 3) & ~3) * 4 + ((2 * t.n_nodes * 8 + 15) & ~15)) +
+    // the one-warp CTAs keep neither the tables nor the constant observation entries in shared memory (LITE)
+    size_t smem = (threads == kTpmSmallThreads ? 0 : (size_t)t.sm_tables_bytes + (size_t)oconst_bytes(t.n_nodes)) +
                   (size_t)(threads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
     return smem;

@@ -137,8 +137,8 @@ def test_oracle_parity_4096_adjacent_random(evg, eo, cfg):
 
 
 def test_oracle_parity_16384_default_kernel_choice(evg, eo, cfg, monkeypatch):
-    """A mid-size batch takes the thread-per-match kernel with one warp per CTA by default (evg_create's choice): every
-    one of the 16,384 matches is followed on the oracle through a full episode with in-place auto-reset."""
+    """A mid-size batch takes the thread-per-match kernel by default (evg_create's choice): every one of the 16,384
+    matches is followed on the oracle through a full episode with in-place auto-reset."""
     monkeypatch.delenv("EVG_STEP_KERNEL", raising=False)
     monkeypatch.delenv("EVG_TPM_SMALL_MAX", raising=False)
     rng = np.random.default_rng(5)
@@ -275,9 +275,9 @@ def test_every_step_kernel_matches_oracle(evg, eo, cfg, monkeypatch, kernel):
     """The step kernels (two lanes per match / one thread per match in 32- and in 128-thread CTAs / one warp per match)
     stay selectable (EVG_STEP_KERNEL, EVG_TPM_SMALL_MAX) for A/B profiling; each must match the oracle, with auto-reset
     and a tail batch (n % 128 != 0)."""
-    if kernel == "tpm128":
-        monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")  # batches this small would take the one-warp-per-CTA instantiation
-        kernel = "tpm"
+    # "tpm" = the one-warp-per-CTA instantiation (forced: by default only batches around 64k matches take it), "tpm128" = 128-thread CTAs
+    monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0" if kernel == "tpm128" else str(1 << 30))
+    kernel = "tpm" if kernel == "tpm128" else kernel
     monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
     rng = np.random.default_rng(31)
     cfg.turn_limit = 70
@@ -295,8 +295,7 @@ def test_fused_agents_equal_agent_kernel_plus_step(evg, eo, cfg, monkeypatch, ke
     batch-size default (warp kernel: rows through the action buffer) and both thread-per-match CTA sizes (fused)."""
     if kernel != "default":
         monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
-        if kernel == "tpm128":
-            monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")
+        monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0" if kernel == "tpm128" else str(1 << 30))
     n = 640
     cfg.auto_reset = 1
     cfg.turn_limit = 60
@@ -352,8 +351,7 @@ def test_scripted_agents_batched_with_autoreset_match_oracle(evg, eo, cfg, monke
     kernel the agents' rows are generated inside the step kernel: a whole self-play turn is ONE launch."""
     if kernel != "default":
         monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
-        if kernel == "tpm128":
-            monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")
+        monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0" if kernel == "tpm128" else str(1 << 30))
     n = 512
     cfg.auto_reset = 1
     try:

@@ -58,9 +58,8 @@ def follow(evg, eo, cfg, n, turns, seed, first, fmt, auto_reset=1):
 @pytest.mark.parametrize("fmt", ["wire", "i16"])
 @pytest.mark.parametrize("kernel", ["warp", "tpm", "tpm128"])
 def test_compact_rows_expand_to_the_oracle_observations(evg, eo, cfg, monkeypatch, kernel, fmt):
-    if kernel == "tpm128":
-        monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0")
-        kernel = "tpm"
+    monkeypatch.setenv("EVG_TPM_SMALL_MAX", "0" if kernel == "tpm128" else str(1 << 30))  # "tpm" = one-warp CTAs, forced
+    kernel = "tpm" if kernel == "tpm128" else kernel
     monkeypatch.setenv("EVG_STEP_KERNEL", kernel)
     cfg.turn_limit = 70
     try:

@@ -49,7 +49,7 @@ def drive(name, n, env_vars, cfg=None, agents=(_capi.AGENT_BASE_RUSH, _capi.AGEN
 
 
 drive("warp-per-match", 96 + 5, {"EVG_STEP_KERNEL": "warp"})
-drive("thread-per-match, 32-thread CTAs", 512 + 37, {"EVG_STEP_KERNEL": "tpm"})
+drive("thread-per-match, 32-thread CTAs", 512 + 37, {"EVG_STEP_KERNEL": "tpm", "EVG_TPM_SMALL_MAX": str(1 << 30)})
 drive("thread-per-match, 128-thread CTAs", 1024 + 37, {"EVG_STEP_KERNEL": "tpm", "EVG_TPM_SMALL_MAX": "0"})
 from test_gpu_generic import write_configs
 import pathlib
