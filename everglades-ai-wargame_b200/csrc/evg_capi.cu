@@ -869,17 +869,17 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
     return EVG_OK;
 }
 
-int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const float* d_b1, const void* d_w2_img,
-                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, int32_t q_transposed, void* stream)
+int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const void* d_w2_img, int32_t hidden, int32_t out_dim,
+                   float* d_q, int32_t q_transposed, void* stream)
 {
     int rc = check_sim(sim, false);
     if (rc) return rc;
-    if (!d_obs || !d_w1_img || !d_b1 || !d_w2_img || !d_b2 || !d_q || rows < 0) return fail(EVG_E_ARG, "evg_policy_mlp: null argument");
-    if (sim->layout.obs_len > EVG_MLP_IN_PAD) return fail(EVG_E_ARG, "evg_policy_mlp: observations of %d values exceed the %d the kernel is tiled for", sim->layout.obs_len, EVG_MLP_IN_PAD);
+    if (!d_obs || !d_w1_img || !d_w2_img || !d_q || rows < 0) return fail(EVG_E_ARG, "evg_policy_mlp: null argument");
+    if (sim->layout.obs_len >= EVG_MLP_IN_PAD) return fail(EVG_E_ARG, "evg_policy_mlp: observations of %d values + the bias input exceed the %d the kernel is tiled for", sim->layout.obs_len, EVG_MLP_IN_PAD);
     if (hidden < 1 || hidden > 64 * EVG_MLP_CHUNK || out_dim < 1 || out_dim > EVG_MLP_OUT_PAD) return fail(EVG_E_ARG, "evg_policy_mlp: hidden %d / out_dim %d outside the kernel's tiling (out <= %d)", hidden, out_dim, EVG_MLP_OUT_PAD);
     if (((uintptr_t)d_w1_img | (uintptr_t)d_w2_img) % 16) return fail(EVG_E_ARG, "evg_policy_mlp: weight images must be 16-byte aligned");
-    const int n_chunks = (hidden + EVG_MLP_CHUNK - 1) / EVG_MLP_CHUNK;
-    cudaError_t e = evg::launch_policy_mlp(d_obs, rows, sim->layout.obs_len, d_w1_img, d_b1, d_w2_img, d_b2, n_chunks, out_dim, d_q, q_transposed, sim->sm_count, (cudaStream_t)stream);
+    const int n_chunks = (hidden + 1 + EVG_MLP_CHUNK - 1) / EVG_MLP_CHUNK;  // + the hidden unit that carries b2
+    cudaError_t e = evg::launch_policy_mlp(d_obs, rows, sim->layout.obs_len, d_w1_img, d_w2_img, n_chunks, out_dim, d_q, q_transposed, sim->sm_count, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_policy_mlp_kernel launch");
     sim->launches += 1;
     return EVG_OK;

@@ -163,8 +163,8 @@ cudaError_t launch_step(const Tables& t, const StepArgs& a, int grid, size_t sme
 cudaError_t launch_rollout(const Tables& t, const StepArgs& a, int n_turns, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, const uint8_t* mask, void* obs, int obs_fmt,
                          int64_t n_envs, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const float* b1, const void* w2_img, const float* b2,
-                              int n_chunks, int out_dim, float* q, int transposed, int sm_count, cudaStream_t stream);
+cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const void* w2_img, int n_chunks, int out_dim, float* q,
+                              int transposed, int sm_count, cudaStream_t stream);
 cudaError_t launch_obs_to_i16(const float* obs, int16_t* out, int64_t n_values, cudaStream_t stream);
 cudaError_t launch_export(const Tables& t, const uint32_t* records, const double* health, int64_t first, int64_t count,
                           EvgEnvState* out, cudaStream_t stream);

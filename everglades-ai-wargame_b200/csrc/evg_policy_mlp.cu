@@ -5,14 +5,17 @@
 // evaluated for every (match, player) row of the observation tensor the step kernel has just written.  One kernel does
 // both layers; the hidden activations never leave the SM:
 //
-//   CTA = 256 threads = one tile of 128 observation rows at a time (UMMA M = 128: TMEM lane i holds row i of the
-//   accumulators; two threads per row, one per half of the columns), persistent over the tiles.
+//   CTA = 512 threads = one tile of 128 observation rows at a time (UMMA M = 128: TMEM lane i holds row i of the
+//   accumulators; four threads per row, one per quarter of the columns), persistent over the tiles.
 //   per tile:  A  <- the tile's float32 observations, converted to bf16 into the K-major 128-byte-swizzled layout
 //              for each chunk c of 192 hidden units (528 -> 3 chunks, zero padded):
 //                 D1[128 x 192]  = A[128 x 128] . W1c^T          8 x tcgen05.mma  (K = 16 each), accumulators in TMEM
-//                 H              = bf16(relu(D1 + b1c))          tcgen05.ld -> registers -> swizzled shared memory
+//                 H              = bf16(relu(D1))                tcgen05.ld -> registers -> swizzled shared memory
 //                 D2[128 x 144] += H[128 x 192] . W2c^T          12 x tcgen05.mma, accumulating over the chunks in TMEM
-//              Q <- D2 + b2                                        tcgen05.ld -> registers -> global (float32)
+//              Q <- D2                                             tcgen05.ld -> registers -> global (float32)
+//   Both biases ride inside the GEMMs (homogeneous coordinates): A carries a column of ones behind the obs_len features
+//   whose weights are b1, and one padding hidden unit is wired to be relu(1) = 1 with b2 as its outgoing weights
+//   (evgsim.policy.pack_mlp builds the images that way), so the epilogues are a ReLU and a store.
 //   The weight chunks W1c / W2c are bf16 IMAGES of the shared-memory operand layout, fetched by the bulk-copy engine
 //   (cp.async.bulk, one instruction per 48 / 54 KB image, completion on an mbarrier) as soon as the MMAs that read the
 //   buffer's previous content have retired: W1(c+1) arrives under the activation epilogue and layer 2 of chunk c,
@@ -31,7 +34,7 @@ namespace evg {
 
 namespace {
 
-constexpr int kMlpThreads = 256;
+constexpr int kMlpThreads = 512;
 constexpr int kTileM = 128;   // observation rows per tile
 constexpr int kInPad = 128;   // input features, padded (obs_len <= 128)
 constexpr int kChunk = 192;   // hidden units per chunk: 3 swizzle atoms of 64
@@ -105,18 +108,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-          "=r"(v[31])
-        : "r"(taddr));
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile(
@@ -143,9 +134,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 
 // q_col_stride == 1: Q[row * q_row_stride + col] (row-major); q_row_stride == 1: Q[col * q_col_stride + row] (transposed)
 __global__ void __launch_bounds__(kMlpThreads, 1)
-evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, const unsigned char* __restrict__ w1_img, const float* __restrict__ b1,
-                      const unsigned char* __restrict__ w2_img, const float* __restrict__ b2, int n_chunks, int out_dim, float* __restrict__ q,
-                      int64_t q_row_stride, int64_t q_col_stride)
+evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, const unsigned char* __restrict__ w1_img,
+                      const unsigned char* __restrict__ w2_img, int n_chunks, int out_dim, float* __restrict__ q, int64_t q_row_stride,
+                      int64_t q_col_stride)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,8 +155,8 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    // my row = TMEM lane 32 * (warp % 4) + lane (a warp reaches the lane quarter warp % 4); my half of the columns = warp / 4
-    const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+    // my row = TMEM lane 32 * (warp % 4) + lane (a warp reaches the lane quarter warp % 4); my quarter of the columns = warp / 4
+    const int r = (warp & 3) * 32 + lane, quarter = warp >> 2;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc1 = make_idesc(kTileM, kChunk), idesc2 = make_idesc(kTileM, kOutPad);
     const uint32_t sA = smem_u32(smem + kSmA), sH = smem_u32(smem + kSmH), sW1 = smem_u32(smem + kSmW1), sW2 = smem_u32(smem + kSmW2);
@@ -177,9 +168,9 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
         bulk_load(smem + kSmW1, w1_img, kW1ChunkBytes, &bar[2]);
         bulk_load(smem + kSmW2, w2_img, kW2ChunkBytes, &bar[3]);
     }
-    // A: a tile's observations -> bf16, swizzled.  Every thread owns 8 of the tile's 2048 16-byte chunks (8 features each):
-    // all 64 loads are issued together into registers (one DRAM round trip), converted and stored later; rows and
-    // features beyond the data are zero.
+    // A: a tile's observations -> bf16, swizzled.  Every thread owns 4 of the tile's 2048 16-byte chunks (8 features each):
+    // all 32 loads are issued together into registers (one DRAM round trip), converted and stored later; feature
+    // `in_dim` is the constant 1 that carries the bias, rows and features beyond that are zero.
     float af[kTileM * (kInPad / 8) / kMlpThreads][8];
     auto load_a = [&](int64_t row0, int nrows) {
 #pragma unroll
@@ -187,7 +178,7 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
             const int i = tid + it * kMlpThreads, ar = i >> 4, k0 = (i & 15) * 8;
             const float* src = obs + (row0 + ar) * in_dim + k0;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) af[it][e] = (ar < nrows && k0 + e < in_dim) ? __ldcs(src + e) : 0.f;
+            for (int e = 0; e < 8; ++e) af[it][e] = (ar < nrows && k0 + e < in_dim) ? __ldcs(src + e) : (k0 + e == in_dim ? 1.f : 0.f);
         }
     };
     auto store_a = [&]() {
@@ -231,23 +222,20 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
                 const int64_t nrow0 = (tile + gridDim.x) * kTileM;
                 load_a(nrow0, rows - nrow0 < kTileM ? (int)(rows - nrow0) : kTileM);  // in flight under the epilogue below
             }
-            // ---- hidden activations of my row, my 96 of the chunk's 192 columns: TMEM -> registers -> bias, ReLU, bf16 -> swizzled H
+            // ---- hidden activations of my row, my 48 of the chunk's 192 columns: TMEM -> registers -> ReLU, bf16 -> swizzled H
             {
-                const float* bc = b1 + c * kChunk;
-#pragma unroll 1
-                for (int j0 = half * (kChunk / 2); j0 < (half + 1) * (kChunk / 2); j0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_base + kTmemD1 + j0, v);
+#pragma unroll
+                for (int j0 = quarter * (kChunk / 4); j0 < (quarter + 1) * (kChunk / 4); j0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(lane_base + kTmemD1 + j0, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // 8 hidden units = one 16-byte chunk of the swizzled row
-                        const float4 ba = __ldg(reinterpret_cast<const float4*>(bc + j0 + 8 * g)), bb = __ldg(reinterpret_cast<const float4*>(bc + j0 + 8 * g + 4));
-                        const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                        float h[8];
+                    for (int g = 0; g < 2; ++g) {  // 8 hidden units = one 16-byte chunk of the swizzled row
+                        uint32_t w[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) h[e] = fmaxf(__uint_as_float(v[8 * g + e]) + bias[e], 0.f);
-                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, j0 + 8 * g)) =
-                            make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack_bf16(fmaxf(__uint_as_float(v[8 * g + 2 * e]), 0.f), fmaxf(__uint_as_float(v[8 * g + 2 * e + 1]), 0.f));
+                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, j0 + 8 * g)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -275,21 +263,26 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tid == 0 && step + 1 < n_steps) bulk_load(smem + kSmW2, w2_img + (size_t)cn * kW2ChunkBytes, kW2ChunkBytes, &bar[3]);
         }
-        // ---- Q = D2 + b2: my row, my half of the columns (80 + 64)
+        // ---- Q = D2: my row, my quarter of the columns (36 = 16 + 16 + 4)
         {
-            float* qr = q + (row0 + r) * q_row_stride;
-            const int jbeg = half ? 80 : 0, jend = half ? kOutPad : 80;
-#pragma unroll 1
-            for (int j0 = jbeg; j0 < jend; j0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(lane_base + kTmemD2 + j0, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (r < nrows) {
+            float* qp = q + (row0 + r) * q_row_stride + (int64_t)(quarter * (kOutPad / 4)) * q_col_stride;
+            const int jq = quarter * (kOutPad / 4);
+            const bool live = r < nrows;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (j0 + e < out_dim) qr[(int64_t)(j0 + e) * q_col_stride] = __uint_as_float(v[e]) + __ldg(b2 + j0 + e);
-                }
+            for (int j0 = 0; j0 < 32; j0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_base + kTmemD2 + jq + j0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 16; ++e, qp += q_col_stride)
+                    if (live && jq + j0 + e < out_dim) *qp = __uint_as_float(v[e]);
             }
+            uint32_t v4[4];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v4[0]), "=r"(v4[1]), "=r"(v4[2]), "=r"(v4[3]) : "r"(lane_base + kTmemD2 + jq + 32));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 4; ++e, qp += q_col_stride)
+                if (live && jq + 32 + e < out_dim) *qp = __uint_as_float(v4[e]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // the next tile's first MMAs overwrite D1 / D2, its conversion overwrites A
@@ -299,8 +292,8 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
 
 }  // namespace
 
-cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const float* b1, const void* w2_img, const float* b2,
-                              int n_chunks, int out_dim, float* q, int transposed, int sm_count, cudaStream_t stream)
+cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const void* w1_img, const void* w2_img, int n_chunks, int out_dim, float* q,
+                              int transposed, int sm_count, cudaStream_t stream)
 {
     if (rows <= 0) return cudaSuccess;
     static bool attr_set = false;
@@ -311,8 +304,8 @@ cudaError_t launch_policy_mlp(const float* obs, int64_t rows, int in_dim, const 
     }
     const int64_t tiles = (rows + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
-    evg_policy_mlp_kernel<<<grid, kMlpThreads, kSmBytes, stream>>>(obs, rows, in_dim, reinterpret_cast<const unsigned char*>(w1_img), b1,
-                                                                   reinterpret_cast<const unsigned char*>(w2_img), b2, n_chunks, out_dim, q,
+    evg_policy_mlp_kernel<<<grid, kMlpThreads, kSmBytes, stream>>>(obs, rows, in_dim, reinterpret_cast<const unsigned char*>(w1_img),
+                                                                   reinterpret_cast<const unsigned char*>(w2_img), n_chunks, out_dim, q,
                                                                    transposed ? 1 : out_dim, transposed ? rows : 1);
     return cudaGetLastError();
 }

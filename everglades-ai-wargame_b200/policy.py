@@ -46,28 +46,32 @@ def _image(mat, rows, cols):
 
 def pack_mlp(w1, b1, w2, b2):
     """w1 [hidden, in], b1 [hidden], w2 [out, hidden], b2 [out] (float32, torch.nn.Linear's layout) ->
-    (w1_img uint8, b1_pad float32, w2_img uint8, b2 float32, hidden, out) as evg_policy_mlp expects them."""
+    (w1_img uint8, w2_img uint8, hidden, out) as evg_policy_mlp expects them.  The biases ride inside the images:
+    input feature `in` is the constant 1 (its weights are b1), hidden unit `hidden` is wired to relu(1) = 1 (its outgoing
+    weights are b2)."""
     w1, b1, w2, b2 = (np.asarray(a, dtype=np.float32) for a in (w1, b1, w2, b2))
     hidden, in_dim = w1.shape
     out = w2.shape[0]
-    assert in_dim <= IN_PAD and out <= OUT_PAD and w2.shape[1] == hidden and b1.shape == (hidden,) and b2.shape == (out,)
-    n_chunks = -(-hidden // CHUNK)
-    w1p = np.zeros((n_chunks * CHUNK, in_dim), dtype=np.float32)
-    w1p[:hidden] = w1
+    assert in_dim < IN_PAD and out <= OUT_PAD and w2.shape[1] == hidden and b1.shape == (hidden,) and b2.shape == (out,)
+    n_chunks = -(-(hidden + 1) // CHUNK)
+    w1p = np.zeros((n_chunks * CHUNK, in_dim + 1), dtype=np.float32)
+    w1p[:hidden, :in_dim] = w1
+    w1p[:hidden, in_dim] = b1
+    w1p[hidden, in_dim] = 1.0
     w2p = np.zeros((out, n_chunks * CHUNK), dtype=np.float32)
     w2p[:, :hidden] = w2
-    b1p = np.zeros(n_chunks * CHUNK, dtype=np.float32)
-    b1p[:hidden] = b1
+    w2p[:, hidden] = b2
     img1 = np.concatenate([_image(w1p[c * CHUNK:(c + 1) * CHUNK], CHUNK, IN_PAD) for c in range(n_chunks)])
     img2 = np.concatenate([_image(w2p[:, c * CHUNK:(c + 1) * CHUNK], OUT_PAD, CHUNK) for c in range(n_chunks)])
-    return img1, b1p, img2, b2.copy(), hidden, out
+    return img1, img2, hidden, out
 
 
 def reference_forward(obs, w1, b1, w2, b2):
-    """What the kernel computes, in numpy: bf16-rounded operands, float32 accumulation, bf16-rounded hidden activations."""
+    """What the kernel computes, in numpy: bf16-rounded operands (weights, biases, observations, hidden activations),
+    float32 accumulation."""
     x = bf16_round(np.asarray(obs, dtype=np.float32))
-    h = np.maximum(x @ bf16_round(w1).T + np.asarray(b1, dtype=np.float32), 0.0).astype(np.float32)
-    return bf16_round(h) @ bf16_round(w2).T + np.asarray(b2, dtype=np.float32)
+    h = np.maximum(x @ bf16_round(w1).T + bf16_round(b1), 0.0).astype(np.float32)
+    return bf16_round(h) @ bf16_round(w2).T + bf16_round(b2)
 
 
 class FusedDQN:
@@ -79,13 +83,11 @@ class FusedDQN:
             lin = [m for m in net if isinstance(m, torch.nn.Linear)]
             assert len(lin) == 2, "expected Sequential(Linear, ReLU, Linear)"
             weights = [t.detach().float().cpu().numpy() for t in (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias)]
-        img1, b1p, img2, b2, self.hidden, self.out_dim = pack_mlp(*weights)
+        img1, img2, self.hidden, self.out_dim = pack_mlp(*weights)
         self.env = env
         dev = env.device
         self._w1 = torch.from_numpy(img1).to(dev)
         self._w2 = torch.from_numpy(img2).to(dev)
-        self._b1 = torch.from_numpy(b1p).to(dev)
-        self._b2 = torch.from_numpy(b2).to(dev)
         self.q = torch.empty((env.num_envs, 2, self.out_dim), dtype=torch.float32, device=dev)
         self.qt = torch.empty((self.out_dim, env.num_envs * 2), dtype=torch.float32, device=dev)
 
@@ -93,8 +95,8 @@ class FusedDQN:
         env = self.env
         obs = env.obs if obs is None else obs
         _capi.check(env._lib.evg_policy_mlp(env._h, C.c_void_p(obs.data_ptr()), env.num_envs * 2, C.c_void_p(self._w1.data_ptr()),
-                                            C.c_void_p(self._b1.data_ptr()), C.c_void_p(self._w2.data_ptr()), C.c_void_p(self._b2.data_ptr()),
-                                            self.hidden, self.out_dim, C.c_void_p(out.data_ptr()), int(transposed), env._stream()))
+                                            C.c_void_p(self._w2.data_ptr()), self.hidden, self.out_dim, C.c_void_p(out.data_ptr()),
+                                            int(transposed), env._stream()))
         return out
 
     def forward(self, obs=None):

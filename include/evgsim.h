@@ -300,18 +300,19 @@ int evg_decode_indices(EvgSim* sim, const int64_t* d_idx, int32_t div, int32_t m
  * — the reference's DQN network, agents/DQN/QNetwork.py:37,42 (105 -> 528 -> 132) — for the observation rows the step
  * has just written (rows = n_envs * 2 for both players), bf16 operands with fp32 accumulation; the hidden activations stay
  * on the SM.  Weights are passed as IMAGES in the kernel's shared-memory operand layout (bf16, K-major, 128-byte swizzle),
- * cut into chunks of EVG_MLP_CHUNK hidden units: for chunk c,
- *     d_w1_img + c * (EVG_MLP_IN_PAD / 64) * EVG_MLP_CHUNK * 128 bytes:  W1[c*CHUNK + n][k], n < CHUNK, k < IN_PAD
- *     d_w2_img + c * (EVG_MLP_CHUNK / 64) * EVG_MLP_OUT_PAD * 128 bytes: W2[o][c*CHUNK + k], o < OUT_PAD, k < CHUNK
+ * cut into chunks of EVG_MLP_CHUNK hidden units, with the biases inside (homogeneous coordinates): input feature obs_len
+ * is the constant 1, hidden unit `hidden` is wired to relu(1 * 1) = 1.  With W1' = [W1 | b1] plus that unit's row, and
+ * W2' = [W2 | b2], for chunk c (ceil((hidden + 1) / CHUNK) chunks):
+ *     d_w1_img + c * (EVG_MLP_IN_PAD / 64) * EVG_MLP_CHUNK * 128 bytes:  W1'[c*CHUNK + n][k], n < CHUNK, k < IN_PAD
+ *     d_w2_img + c * (EVG_MLP_CHUNK / 64) * EVG_MLP_OUT_PAD * 128 bytes: W2'[o][c*CHUNK + k], o < OUT_PAD, k < CHUNK
  * element (row r, column k) of a [R x K] block at byte (k/64)*R*128 + r*128 + ((((k%64)/8) ^ (r%8)) * 16) + (k%8)*2, zero
- * padded; d_b1 has ceil(hidden / CHUNK) * CHUNK floats (zero padded), d_b2 out_dim floats.  evgsim.policy.pack_mlp builds
- * them from a torch module.  q_transposed != 0 writes d_q as [out_dim][rows] instead (each output's values for all rows
- * contiguous): the layout evg_decode_dqn_layout reads coalesced. */
+ * padded.  evgsim.policy.pack_mlp builds them from a torch module.  q_transposed != 0 writes d_q as [out_dim][rows]
+ * instead (each output's values for all rows contiguous): the layout evg_decode_dqn_layout reads coalesced. */
 #define EVG_MLP_IN_PAD 128
 #define EVG_MLP_CHUNK 192
 #define EVG_MLP_OUT_PAD 144
-int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const float* d_b1, const void* d_w2_img,
-                   const float* d_b2, int32_t hidden, int32_t out_dim, float* d_q, int32_t q_transposed, void* stream);
+int evg_policy_mlp(EvgSim* sim, const float* d_obs, int64_t rows, const void* d_w1_img, const void* d_w2_img, int32_t hidden, int32_t out_dim,
+                   float* d_q, int32_t q_transposed, void* stream);
 
 /* Reward shaping of the reference's training scripts (utils/reward_shaping.py:17-56) on the step's outputs:
  * d_out float32 [n_envs][2].  turnNum (steps played before this one) is read from the observation's turn
