@@ -72,14 +72,20 @@ constexpr int kMoveUnroll = EVG_TPM_MOVE_UNROLL, kCaptureUnroll = EVG_TPM_CAPTUR
 // job: refill_health below)
 __device__ __noinline__ void reset_row(const Tables& S, uint32_t* R, int n_nodes, uint32_t* X = nullptr)
 {
+    // (rolled loops on purpose: this runs for one lane at a time when matches end at different times, and every
+    // instruction of it that is fetched evicts one of the hot loop's from the instruction cache)
+#pragma unroll 1
     for (int L = 0; L < kGroupLanes; ++L) {
         R[2 * L] = S.init_w0[L];
         R[2 * L + 1] = S.init_w1[L];
     }
+#pragma unroll 1
     for (int n = 1; n <= n_nodes; ++n) R[kRecNode0 + n - 1] = S.init_node[n];
     if (X) {  // EVG_AUTORESET_NEXT: the observation shows the new match, so its node sums are needed too
         const int nn = n_nodes + 1;
+#pragma unroll 1
         for (int i = 0; i < 2 * nn; ++i) X[32 * i] = 0;
+#pragma unroll 1
         for (int L = 0; L < kGroupLanes; ++L) {
             const uint32_t w0 = R[2 * L], cnt = __popc(R[2 * L + 1] & 0xFFFFu);
             X[32 * ((L >= EVG_NUM_GROUPS ? nn : 0) + (w0 & W0_LOC_MASK))] += cnt | (cnt * S.g_control[L]) << 10 | 1u << 24;

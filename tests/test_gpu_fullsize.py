@@ -91,3 +91,28 @@ def test_trajectories_do_not_depend_on_batch_or_shard(big):
         po, pr, pd, _ = part.step_agents()
         assert bool((fo[1000:1000 + 4096] == po).all()) and bool((fr[1000:1000 + 4096] == pr).all())
         assert bool((fd[1000:1000 + 4096] == pd).all())
+
+
+def test_wire_rows_equal_float32_observations_at_full_size(big):
+    """1,048,576 matches stepped twice — float32 vectors and packed wire rows — from the same action stream: at turns
+    early, mid-game and across the turn-150 reset EVERY row expands to exactly the float32 observation, reward and done
+    flag of its match (evgsim.wire.expand, in slices of 131,072 rows)."""
+    torch, evg, cfg = big["torch"], big["evg"], big["cfg"]
+    from evgsim import wire
+    a = evg.BatchedEvergladesEnv(N, seed=77, config=cfg, auto_reset=1)
+    b = evg.BatchedEvergladesEnv(N, seed=77, config=cfg, auto_reset=1)
+    a.reset()
+    b.reset(obs_format="wire")
+    checked = 0
+    for t in range(1, 153):
+        acts = a.random_actions()
+        obs, rew, done, info = a.step(acts)
+        rows, _, _, _ = b.step(acts, obs_format="wire")
+        if t in (1, 2, 40, 75, 110, 150, 151, 152):
+            for lo in range(0, N, 1 << 17):
+                o, r, d, s = wire.expand(rows[lo:lo + (1 << 17)].cpu().numpy(), cfg)
+                assert np.array_equal(o, obs[lo:lo + (1 << 17)].cpu().numpy()), (t, lo)
+                assert np.array_equal(r, rew[lo:lo + (1 << 17)].cpu().numpy()) and np.array_equal(d, done[lo:lo + (1 << 17)].cpu().numpy()), (t, lo)
+                assert np.array_equal(s, info["status"][lo:lo + (1 << 17)].cpu().numpy()), (t, lo)
+            checked += 1
+    assert checked == 8 and a.episode_stats() == b.episode_stats()
