@@ -18,3 +18,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 bash tools/ncu_capture.sh r2_final_1m staggered 160 1048576
 bash tools/ncu_capture.sh r2_final_256k staggered 160 262144
 ls -la $O | tail -30
+NCU_SKIP=60 bash tools/ncu_mlp.sh > /dev/null 2>&1
