@@ -849,7 +849,10 @@ bool tpm_has_small(const Tables& t) { return pick(t) == V_FAST; }
 
 static size_t tpm_smem_bytes(const Tables& t, int threads)
 {
-    // the one-warp CTAs keep neither the tables nor the constant observation entries in shared memory (LITE)
+    // the one-warp CTAs keep neither the tables nor the constant observation entries in shared memory (LITE).
+    // DemoMap, 128-thread CTAs: 65,696 B; three CTAs + the driver's 1 KiB each = 195.5 KiB, inside the SM's 196 KiB
+    // shared-memory configuration.  One more KB per CTA selects the 228 KiB configuration, L1 drops from 60 to 28 KiB
+    // and the step kernel loses 15 %: do not grow this.
     size_t smem = (threads == kTpmSmallThreads ? 0 : (size_t)t.sm_tables_bytes + (size_t)oconst_bytes(t.n_nodes)) +
                   (size_t)(threads / 32) * (32 * t.tpm_pitch + 64 * (t.n_nodes + 1) + t.tpm_pool_words) * 4;
     if (const char* pad = getenv("EVG_TPM_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiments (profiles/README.md)
