@@ -77,12 +77,13 @@ __device__ __forceinline__ void load_group(const double* __restrict__ hp, int si
     }
 }
 
-// One target group: apply the damage histogram to its units, write the touched quads back.  Returns the new
-// alive mask and the observation's avg health (server.py:573-643, :480-491).
+// Unit slots [0, size) of one target group (the whole group, or one 8-slot segment of it): apply the damage histogram
+// to the units, write the touched quads back.  Returns the new alive mask; hv holds the new health values
+// (server.py:573-643).  hist[tb + r] is the damage aimed at the r-th unit of the range that was alive before combat.
 template <int MAXSZ, typename HistT, bool FMA_ONLY = false>
-__device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
+__device__ __forceinline__ uint32_t apply_units(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
                                                 const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
-                                                int* avg_out, double rcp = 0.0)
+                                                double rcp = 0.0)
 {
     // pass 1: damage aimed at every alive unit.  infliction[uid]: uid -> r-th unit alive before combat
     uint32_t dv[MAXSZ];
@@ -131,9 +132,37 @@ __device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double 
 #pragma unroll
     for (int u = 0; u < MAXSZ; u += 4)  // one 32-byte store per quad that was hit (padding slots keep what was read)
         if (dv[u] | dv[u + 1] | dv[u + 2] | dv[u + 3]) stg256(hp + u, hv[u], hv[u + 1], hv[u + 2], hv[u + 3]);
+    return alive;
+}
+
+// One target group handled by one lane: the new alive mask and the observation's avg health (server.py:480-491)
+template <int MAXSZ, typename HistT, bool FMA_ONLY = false>
+__device__ __forceinline__ uint32_t apply_group(double* __restrict__ hp, double (&hv)[MAXSZ], int size, uint32_t alive0,
+                                                const HistT* __restrict__ hist, int tb, const double* __restrict__ ltab, double divisor,
+                                                int* avg_out, double rcp = 0.0)
+{
+    const uint32_t alive = apply_units<MAXSZ, HistT, FMA_ONLY>(hp, hv, size, alive0, hist, tb, ltab, divisor, rcp);
     const double hsum = np_sum_regs<MAXSZ>(hv, size);
     *avg_out = alive ? int_quotient(hsum, __popc(alive)) : 0;  // int((health*1.)/units_alive), :491
     return alive;
+}
+
+// numpy's pairwise sum of a group of more than 8 units whose slots [0, 8) are lo[] and [8, size) are hi[] (two lanes' segments)
+template <int HI>
+__device__ __forceinline__ double np_sum_split(const double (&lo)[8], const double (&hi)[HI], int size)
+{
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r[k] = lo[k];
+        if (HI == 8 && size == 16) r[k] = __dadd_rn(lo[k], hi[k]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int i = 0; i < (HI < 7 ? HI : 7); ++i)
+        if (8 + i < size && size < 16) res = __dadd_rn(res, hi[i]);  // remainder, sequential
+    return res;
 }
 
 // k-th (0-based) set bit of a 24-bit mask

@@ -62,6 +62,9 @@
 #define EVG_TPM_REQUEST_AT 1  // where the next batch's records are requested: 0 before the observation phase, 1 before movement
 #endif
 
+#ifndef EVG_TPM_SEG
+#define EVG_TPM_SEG 1
+#endif
 namespace evg {
 
 namespace {
@@ -174,6 +177,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     // of 19.7: 14 CTAs per SM instead of 11, 65,536 matches in ONE wave) — and the next-batch register pipeline, which a
     // CTA that runs one or two batches has no use for, gives its 71 registers back.
     constexpr bool LITE = THREADS == kTpmSmallThreads;
+    // SEG (compile-time map): combat applies damage in segments of 8 unit slots, a group of 9..MAXSZ slots on two lanes
+    constexpr bool SEG = NODES != 0 && EVG_TPM_SEG != 0 && MAXSZ > 8;
+    constexpr int HVN = SEG ? 8 : MAXSZ;
     constexpr bool PIPE = NODES != 0 && EVG_TPM_PIPE != 0 && !LITE;
     uint4 nxt[16];
     uint32_t nxa[7];
@@ -390,7 +396,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             }
             // a fighting group with more than 8 units alive draws from two Philox blocks: its second block becomes
             // a work item of its own (a lane running both blocks would hold up its whole round for a second pass)
-            if (S.n_big <= 8)
+            // (SEG, the compile-time map: EVERY fighting group of more than 8 unit slots has a second item, which also
+            // applies the damage to slots 8.. — the round's apply then runs over 8 slots per lane instead of 12)
+            if (SEG) xm = fm & S.big_mask;
+            else if (S.n_big <= 8)
                 for (uint32_t m = fm & S.big_mask; m; m &= m - 1) {
                     const int L = __ffs(m) - 1;
                     if (__popc(R[2 * L + 1] & 0xFFFFu) > 8) xm |= 1u << L;
@@ -465,21 +474,29 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             uint32_t* Rm = wrow + (size_t)m * P;
             const uint32_t* Xm = wx + m;
             int L = 0, side = 0, x = 1, tb = 0;
+            uint32_t alive_seg = 0;
             uint32_t w0 = 0, w1 = 0, gf = 0;
-            double hv[MAXSZ];
+            double hv[HVN];
             double* hp = A.health;
             const int nf = __popc(fmm);
-            const bool extra = act && q - pm >= nf;  // a second draw block: no health update of its own
+            const bool extra = act && q - pm >= nf;  // a second draw block (SEG: and the group's unit slots from 8 on)
+            int seg_size = 0;
             const bool own_item = act && !extra;
             __syncwarp();  // pool zeroed
             if (act) {
                 L = extra ? kth_set_bit(xmm, q - pm - nf) : kth_set_bit(fmm, q - pm);
                 EVG_CHECK(L >= 0 && L < kGroupLanes && (!act || (m >= m_begin && m < m_end)));
                 gf = S.g_fight[L];  // health slot | unit slots << 12 | damage << 17 | unit type << 25
-                if (!extra) {
+                if (SEG) {
+                    const int size = (int)((gf >> 12) & 31u);
+                    seg_size = extra ? size - 8 : min(size, 8);
+                    hp = A.health + (warp_env0 + m) * S.health_slots + (gf & 0xFFFu) + (extra ? 8 : 0);
+                    EVG_CHECK(warp_env0 + m < A.n_envs && (!extra || size > 8) && (int)(gf & 0xFFFu) + (size + 3) / 4 * 4 <= S.health_slots);
+                    load_group<HVN>(hp, seg_size, hv);  // consumed after the draws
+                } else if (!extra) {
                     hp = A.health + (warp_env0 + m) * S.health_slots + (gf & 0xFFFu);
                     EVG_CHECK(warp_env0 + m < A.n_envs && (int)(gf & 0xFFFu) + ((int)((gf >> 12) & 31u) + 3) / 4 * 4 <= S.health_slots);
-                    load_group<MAXSZ>(hp, (int)((gf >> 12) & 31u), hv);  // consumed after the draws
+                    load_group<HVN>(hp, (int)((gf >> 12) & 31u), hv);  // consumed after the draws
                 }
                 side = L >= EVG_NUM_GROUPS ? 1 : 0;
                 const int gg = L - side * EVG_NUM_GROUPS;
@@ -495,7 +512,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 const uint32_t n = (opp >> 16) & 0xFFu;                        // opposing units at the node
                 const uint32_t mb = (ubm & 0xFFFFu) - ubase, mb0 = ubm >> 16;  // my match's pool entries; its side-0 count
                 const uint32_t hb = mb + (side ? 0u : mb0) + (opp >> 24);      // opposing histogram base at this node
-                if (!extra) {
+                if (SEG || !extra) {
                     tb = (int)(mb + (side ? mb0 : 0u) + (own >> 24));          // my side's base at this node
                     // my group's range starts after the groups listed before it (arrival order, then gid:
                     // node.groups[pid], :198,690-691); sibling counts are still pre-combat here
@@ -510,7 +527,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 // its type's damage to infliction[uid]; 8 draws of 16 bits per Philox block (oracle/tape.py).
                 // This item draws for units [8 * jb, 8 * jb + nd)
                 const uint32_t jb = extra ? 1u : 0u;
-                const uint32_t nd = extra ? cnt - 8u : (((xmm >> L) & 1u) ? 8u : cnt);
+                const uint32_t nd = SEG ? (extra ? (cnt > 8u ? cnt - 8u : 0u) : min(cnt, 8u)) : (extra ? cnt - 8u : (((xmm >> L) & 1u) ? 8u : cnt));
                 const uint32_t dmg = (gf >> 17) & 0xFFu;
                 const uint2 te = *reinterpret_cast<const uint2*>(Rm + kRecTurn);  // turn, episode
                 const uint32_t turn_m = te.x + 1u, ep_m = te.y;
@@ -531,23 +548,54 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             }
             __syncwarp();
             // apply, :573-643: both sides drew on pre-combat counts (:572); one lane updates one whole group
-            if (own_item) {
+            if (SEG ? act : own_item) {
+                const int type = (int)(gf >> 25);
+                constexpr bool FMA_ONLY = NODES != 0;  // the compile-time map's kernel is only picked when Tables::fast_div holds
                 const uint32_t nwd = Rm[kRecNode0 + x - 1];
                 const int cb = (int)(int8_t)((nwd >> 16) & 0xFFu);
                 const int bonus = (cb == side ? 1 : 0) + ((S.node_flags[x] >> 2) & 1);
-                const int type = (int)(gf >> 25);
-                const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const int ti = (type * nn + x) * 3 + bonus;
-                constexpr bool FMA_ONLY = NODES != 0;  // the compile-time map's kernel is only picked when Tables::fast_div holds
+                const double divisor = __dadd_rn(S.unit_armor[type], __dmul_rn((double)bonus, S.node_def[x]));
                 const double* ltab = FMA_ONLY || S.fast_div ? nullptr : S.loss_tab + (size_t)ti * kLossD;
                 const double rcp = FMA_ONLY || S.fast_div ? __ldg(S.rcp_tab + ti) : 0.0;
                 EVG_CHECK(tb >= 0 && (uint32_t)tb + (uint32_t)__popc(w1 & 0xFFFFu) <= uround && ti >= 0);
-                int avg;
-                const uint32_t alive = apply_group<MAXSZ, HistT, FMA_ONLY>(hp, hv, (int)((gf >> 12) & 31u), w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
-                                                                           tb, ltab, divisor, &avg, rcp);
-                // alive == 0: destroyed, leaves the node list (:623-627)
-                *reinterpret_cast<uint2*>(Rm + 2 * L) = make_uint2((w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT,
-                                                                   (w1 & 0xFFFF0000u) | alive);
+                if constexpr (SEG) {
+                    // my segment: slots [0, 8) of the group, or [8, size) whose histogram entries follow the first segment's
+                    alive_seg = apply_units<HVN, HistT, FMA_ONLY>(hp, hv, seg_size, extra ? (w1 >> 8) & 0xFFu : w1 & 0xFFu, reinterpret_cast<const HistT*>(pool),
+                                                                  extra ? tb + __popc(w1 & 0xFFu) : tb, ltab, divisor, rcp);
+                } else {
+                    int avg;
+                    const uint32_t alive = apply_group<HVN, HistT, FMA_ONLY>(hp, hv, (int)((gf >> 12) & 31u), w1 & 0xFFFFu, reinterpret_cast<const HistT*>(pool),
+                                                                             tb, ltab, divisor, &avg, rcp);
+                    // alive == 0: destroyed, leaves the node list (:623-627)
+                    *reinterpret_cast<uint2*>(Rm + 2 * L) = make_uint2((w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT,
+                                                                       (w1 & 0xFFFF0000u) | alive);
+                }
+            }
+            if constexpr (SEG) {
+                // a group of more than 8 slots: its first lane collects the second segment's outcome, then alive mask and
+                // avg health (numpy's pairwise sum over all of its slots, :480-491) as for any other group
+                const bool big = own_item && ((xmm >> L) & 1u);
+                uint32_t alive_hi = 0;
+                double hi[MAXSZ - 8];
+#pragma unroll
+                for (int k = 0; k < MAXSZ - 8; ++k) hi[k] = 0.0;
+                if (__ballot_sync(0xFFFFFFFFu, extra)) {
+                    const int src = big ? pm + nf + __popc(xmm & ((1u << L) - 1u)) - base : lane;
+                    EVG_CHECK(src >= 0 && src < 32 && (!big || src < nround));
+                    alive_hi = __shfl_sync(0xFFFFFFFFu, alive_seg, src);
+#pragma unroll
+                    for (int k = 0; k < MAXSZ - 8; ++k) hi[k] = __shfl_sync(0xFFFFFFFFu, hv[k], src);
+                }
+                if (own_item) {
+                    const int size = (int)((gf >> 12) & 31u);
+                    const uint32_t alive = alive_seg | (big ? alive_hi << 8 : 0u);
+                    const double hsum = big ? np_sum_split<MAXSZ - 8>(hv, hi, size) : np_sum_regs<HVN>(hv, size);
+                    const int avg = alive ? int_quotient(hsum, __popc(alive)) : 0;  // int((health*1.)/units_alive), :491
+                    // alive == 0: destroyed, leaves the node list (:623-627)
+                    *reinterpret_cast<uint2*>(Rm + 2 * L) = make_uint2((w0 & ~(127u << W0_AVG_SHIFT)) | ((uint32_t)avg & 127u) << W0_AVG_SHIFT,
+                                                                       (w1 & 0xFFFF0000u) | alive);
+                }
             }
             __syncwarp();
             m_begin = m_end;
@@ -839,7 +887,8 @@ enum Variant { V_FAST = 0, V_GENERIC8, V_GENERIC16 };
 
 Variant pick(const Tables& t)
 {
-    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == kFastPitch && t.fast_div) return V_FAST;
+    // (n_big <= 8: every group of more than 8 slots can have its second work item, a match's items still fit one round)
+    if (t.n_nodes == 11 && t.max_group_size <= 12 && !t.tpm_hist16 && t.tpm_pitch == kFastPitch && t.fast_div && t.n_big <= 8) return V_FAST;
     return t.tpm_hist16 ? V_GENERIC16 : V_GENERIC8;
 }
 

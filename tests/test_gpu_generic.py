@@ -144,3 +144,48 @@ def test_simulators_of_different_configurations_coexist(tmp_path, kernel, monkey
             oobs, orew, odone = ora.step(acts)
             assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
             assert np.array_equal(done.cpu().numpy(), odone), t
+
+
+@pytest.mark.parametrize("sizes", [
+    [12, 9, 10, 11, 12, 9, 10, 11, 4, 4, 4, 1],     # 8 groups of 9..12 slots: every one fights on two lanes (segments of 8 slots)
+    [8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 9],           # budget 97: the remainder group has ONE slot in its second segment
+    [10, 10, 10, 10, 10, 10, 10, 10, 10, 3, 3, 3],  # 9 groups above 8 slots: more than a round can split, run-time-sized kernel
+    [12, 1, 2, 3, 4, 5, 6, 7, 8, 12, 12, 12],       # every size below 8 next to four full ones
+])
+@pytest.mark.parametrize("lite", [0, 1])
+def test_demomap_loadouts_with_groups_split_over_two_lanes(sizes, lite, monkeypatch):
+    """DemoMap with other loadouts: the compile-time-map kernel updates a group of more than 8 unit slots on two lanes
+    (slots [0, 8) and [8, size)), the first of which rebuilds numpy's pairwise sum and the alive mask from both — for
+    second segments of 1..4 slots, with up to 8 such groups per player side by side with small ones; fp64 health, alive
+    masks, averages and everything else must stay equal to the oracle's through fights and auto-resets."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
+    monkeypatch.setenv("EVG_TPM_SMALL_MAX", str(1 << 30) if lite else "0")
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+    from oracle import evg_oracle as eo
+
+    cfg = evgsim.load_config(auto_reset=1, turn_limit=70)
+    for p in (0, 1):
+        for gi, sz in enumerate(sizes):
+            cfg.group_size[p][gi] = sz
+    n = 640
+    env = evgsim.BatchedEvergladesEnv(n, seed=sum(sizes), config=cfg, auto_reset=1, env_id_offset=3)
+    ora = eo.OracleBatch(cfg, n, seed=sum(sizes), first=3)
+    eo.fought_slots(clear=True)
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset().astype(np.float32))
+    rng = np.random.default_rng(len(sizes) + sizes[1])
+    deaths = 0
+    for t in range(150):
+        acts = adjacent_actions(rng, ora.states, cfg)
+        obs, rew, done, info = env.step(acts)
+        oobs, orew, odone = ora.step(acts)
+        assert np.array_equal(done.cpu().numpy(), odone), t
+        assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
+        assert np.array_equal(rew.cpu().numpy(), orew.astype(np.float32)), t
+        deaths += int((ora.states["groups"]["destroyed"]).sum())
+        if t % 30 == 29:
+            assert_states_equal(env.get_state(), ora.states, "turn %d" % (t + 1))
+    assert deaths > 0
+    st = env.episode_stats()
+    assert st["episodes"] >= 2 * n and st["fought_unit_slots"] == eo.fought_slots()
