@@ -523,9 +523,10 @@ int evg_reset(EvgSim* sim, const uint8_t* d_mask, float* d_obs, void* stream) { 
 // chunks; all the per-match arrays are offset here, the kernel adds `first` to the global match ids)
 static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_actions, int8_t* d_actions_out, void* d_obs,
                      float* d_reward, uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream, int64_t first = 0,
-                     int64_t count = -1, int obs_fmt = EVG_OBS_F32, int sched_slot = 0)
+                     int64_t count = -1, int obs_fmt = EVG_OBS_F32, int sched_slot = 0, int n_turns = 1)
 {
     evg::StepArgs a;
+    a.n_turns = n_turns;
     a.agent[0] = agent0;
     a.agent[1] = agent1;
     a.actions_out = d_actions_out;
@@ -564,7 +565,7 @@ static int step_impl(EvgSim* sim, int agent0, int agent1, const int8_t* d_action
                                   : evg::launch_step_tpm(sim->tables, a, sim->tpm_threads, sim->tpm_smem, sim->tpm_grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "evg_step kernel launch");
     sim->launches += 1;
-    if (count < 0 || first == 0) sim->steps += 1;
+    if (count < 0 || first == 0) sim->steps += n_turns;
     return EVG_OK;
 }
 
@@ -614,12 +615,14 @@ int evg_rollout(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int32_t n_turns
     for (int p = 0; p < 2; ++p)
         if (ag[p] <= EVG_AGENT_EXTERNAL || ag[p] > EVG_AGENT_SWARM) return fail(EVG_E_ARG, "evg_rollout: player %d needs a scripted agent, got %d", p, ag[p]);
     const bool random_big_map = (agent_p0 == EVG_AGENT_RANDOM || agent_p1 == EVG_AGENT_RANDOM) && sim->cfg.n_nodes > evg::kAgentMaxNodes;
-    if (sim->use_tpm || random_big_map) {  // one launch (or agent kernel + step) per turn; a caller may capture this in a CUDA graph
+    if (n_turns == 0) return EVG_OK;
+    if (random_big_map) {  // agent kernel + step per turn; a caller may capture this in a CUDA graph
         for (int k = 0; k < n_turns; ++k)
             if ((rc = evg_step_agents(sim, agent_p0, agent_p1, d_actions, d_obs, d_reward, d_done, d_status, d_scores, stream))) return rc;
         return EVG_OK;
     }
-    if (n_turns == 0) return EVG_OK;
+    if (sim->use_tpm)  // one launch: a CTA keeps each of its batches in shared memory for all n_turns
+        return step_impl(sim, agent_p0, agent_p1, d_actions, d_actions, d_obs, d_reward, d_done, d_status, d_scores, stream, 0, -1, EVG_OBS_F32, 0, n_turns);
     evg::StepArgs a;
     memset(&a, 0, sizeof(a));
     a.agent[0] = agent_p0;

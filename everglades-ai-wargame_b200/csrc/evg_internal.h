@@ -131,6 +131,7 @@ struct StepArgs {
     const float* oconst_dev;  // behind it: the constant observation entries as floats (oconst_bytes(n_nodes), filled by evg_bind)
     int64_t env_first;        // thread-per-match kernel: this launch covers matches [env_first, env_first + n_envs) of the
                               // simulator (all pointers above are already offset); 0 for a whole-batch launch
+    int32_t n_turns;          // thread-per-match kernel, both players scripted: game turns this launch plays (evg_rollout); else 1
     unsigned* sched;          // thread-per-match kernel: {batches handed out after the first wave, CTAs finished}, zero between launches
     uint2* agent_state;       // per (match, player) state of the observation-driven scripted agents (bind slot EVG_BIND_AGENTS)
     int32_t obs_fmt;          // EVG_OBS_F32: `obs` is float32[n][2][obs_len]; EVG_OBS_WIRE: packed rows of wire_bytes(n_nodes)

@@ -288,6 +288,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     int s0 = 0, s1 = 0, status = 0;
     bool done = false;
     float r0 = 0.f, r1 = 0.f;
+    bool reset_now = false;
+    // Fully scripted self-play (evg_rollout): the batch stays in its rows for A.n_turns game turns — only the last one
+    // pays for the observations and the record write-back, none for a launch.  Every other call runs the body once.
+    const int n_turns = AGENTS ? A.n_turns : 1;
+#pragma unroll 1
+    for (int tt = 0; tt < n_turns; ++tt) {
+    const bool last = !AGENTS || tt + 1 == n_turns;
+    if (AGENTS) { s0 = 0; s1 = 0; status = 0; }
     if (valid) {
         turn = R[kRecTurn] + 1u;  // server.py:214
         episode = R[kRecEpisode];
@@ -604,7 +612,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
 
     EVG_PHASE_SYNC(2);
 #if EVG_TPM_REQUEST_AT == 1
-    if (PIPE) have = request(next_batch);
+    if (PIPE && last) have = request(next_batch);
 #endif
     if (valid) {
         // ---- movement (server.py:656-706) fused with the per-(side,node) sums capture and observations need:
@@ -699,13 +707,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             r0 = __fdiv_rn((float)s0, S.max_score_f);
             r1 = __fdiv_rn((float)s1, S.max_score_f);
         }
-        reinterpret_cast<float2*>(A.reward)[env] = make_float2(r0, r1);
-        A.done[env] = done ? 1 : 0;
-        if (A.status) A.status[env] = (uint8_t)status;
-        if (A.scores) reinterpret_cast<int2*>(A.scores)[env] = make_int2(s0, s1);
-
+        if (last) {
+            reinterpret_cast<float2*>(A.reward)[env] = make_float2(r0, r1);
+            A.done[env] = done ? 1 : 0;
+            if (A.status) A.status[env] = (uint8_t)status;
+            if (A.scores) reinterpret_cast<int2*>(A.scores)[env] = make_int2(s0, s1);
+        }
     }
-    const bool reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
+    reset_now = valid && done && S.auto_reset != EVG_AUTORESET_OFF;
     // ---- episode end: statistics, aggregated over the warp before touching the global counters
     if (const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, reset_now)) {
         episode_stats(A.stats, reset_now, s0, s1, turn, status, lane);
@@ -716,6 +725,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         turn = 0;
         episode += 1;
     }
+    if (AGENTS && !last) {  // on to the next turn of the rollout (nobody sees this turn's terminal observation)
+        if (reset_now && S.auto_reset == EVG_AUTORESET_TERMINAL) {
+            reset_row(S, R, n_nodes);
+            turn = 0;
+            episode += 1;
+        }
+        if (valid) {
+            R[kRecTurn] = turn;
+            R[kRecEpisode] = episode;
+        }
+        __syncwarp();
+    }
+    }  // turns of a rollout
 
 #if EVG_TPM_REQUEST_AT == 0
     if (PIPE) have = request(next_batch);  // in flight across the barrier

@@ -217,12 +217,14 @@ class BatchedEvergladesEnv:
         return self.obs, self.reward, self.done, info
 
     def rollout(self, turns, agent0=_capi.AGENT_RANDOM, agent1=_capi.AGENT_RANDOM, graph_turns=50):
-        """`turns` self-play turns with both players scripted on the device.
+        """`turns` self-play turns with both players scripted on the device, in ONE launch of evg_rollout.
 
-        Small batches (warp-per-match kernel) run all the turns in ONE launch of evg_rollout's multi-turn kernel.  Above
-        that, a turn is one fused launch, and since mid-size batches are still launch-bound the turns are captured once
-        into a CUDA graph of `graph_turns` turns and replayed; what is left over runs as plain launches.  Results are those of calling step_agents(agent0, agent1) `turns` times: the tensors hold the last
-        turn's outputs, episode statistics accumulate on the device.  graph_turns=0 disables the graph."""
+        Small batches run the warp-per-match multi-turn kernel (a warp keeps its match for the whole rollout), larger ones
+        the thread-per-match kernel, whose CTAs keep each batch of 128 matches in shared memory for all the turns: only the
+        last turn pays for observations and the record write-back, none for a launch.  Results are those of calling
+        step_agents(agent0, agent1) `turns` times: the tensors hold the last turn's outputs, episode statistics accumulate
+        on the device.  (Only the random agent on maps of more than 15 nodes still runs turn by turn: agent kernel + step,
+        captured into a CUDA graph of `graph_turns` turns; graph_turns=0 disables the graph.)"""
         if not self._is_reset:
             raise RuntimeError("call reset() before rollout()")
         torch = _torch()
@@ -230,8 +232,7 @@ class BatchedEvergladesEnv:
         if _capi.AGENT_EXTERNAL in (agent0, agent1):
             raise ValueError("rollout() needs both players scripted (AGENT_RANDOM / AGENT_BASE_RUSH / AGENT_SWARM)")
         left = int(turns)
-        if self._lib.evg_step_kernel_kind(self._h) == 0 and not (self.num_nodes > 15 and _capi.AGENT_RANDOM in (agent0, agent1)):
-            # small batch on the warp-per-match kernel: evg_rollout runs all the turns in ONE launch
+        if not (self.num_nodes > 15 and _capi.AGENT_RANDOM in (agent0, agent1)):
             _capi.check(self._lib.evg_rollout(self._h, agent0, agent1, left, C.c_void_p(self._actions.data_ptr()),
                                               C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.reward.data_ptr()),
                                               C.c_void_p(self.done.data_ptr()), C.c_void_p(self.status.data_ptr()),

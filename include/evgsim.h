@@ -233,9 +233,11 @@ int evg_step_agents(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int8_t* d_a
 
 /* `n_turns` turns of fully scripted self-play (both agents != EVG_AGENT_EXTERNAL) with the results of evg_step_agents
  * called n_turns times: the output arrays hold the last turn's values, statistics accumulate, d_actions (required) is
- * scratch for the generated rows.  Small batches (evg_step_kernel_kind() == 0) run ALL the turns in ONE launch — a warp
- * keeps its match for the whole rollout, so a turn costs neither a launch nor an action-buffer pass; larger batches run
- * one fused launch per turn (capture the call in a CUDA graph to shed the launch overhead). */
+ * scratch for the generated rows.  ALL the turns run in ONE launch: small batches (evg_step_kernel_kind() == 0) on the
+ * multi-turn warp-per-match kernel (a warp keeps its match for the whole rollout), larger ones on the thread-per-match
+ * kernel, whose CTAs keep each batch in shared memory for all n_turns — a turn costs neither a launch nor an action-buffer
+ * pass, and only the last one writes observations and records.  (Only EVG_AGENT_RANDOM on maps of more than 15 nodes
+ * runs turn by turn: agent kernel + step.) */
 int evg_rollout(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int32_t n_turns, int8_t* d_actions, float* d_obs, float* d_reward,
                 uint8_t* d_done, uint8_t* d_status, int32_t* d_scores, void* stream);
 

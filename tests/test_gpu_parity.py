@@ -415,27 +415,32 @@ def test_import_rejects_out_of_range_fields(evg, cfg):
     assert_states_equal(env.get_state(), st, "re-import")
 
 
-@pytest.mark.parametrize("n", [600, 16384 + 5])
-def test_rollout_from_a_cuda_graph_equals_plain_turns(evg, cfg, n):
-    """BatchedEvergladesEnv.rollout replays the self-play turn from a CUDA graph (50 turns per replay + a remainder of
-    plain launches): same final state, outputs and statistics as step_agents called turn by turn — on the warp-per-match
-    kernel (agent kernel + step) and on the thread-per-match kernel (agents fused into the step)."""
+@pytest.mark.parametrize("n,mode", [(600, 1), (16384 + 5, 1), (16384 + 5, 2), (60000, 1), (60000, 2)])
+def test_multi_turn_rollout_equals_plain_turns(evg, cfg, n, mode):
+    """BatchedEvergladesEnv.rollout plays K scripted self-play turns in ONE launch — the warp-per-match multi-turn kernel
+    (600 matches), the 128-thread thread-per-match kernel (16,389: a partial last warp) and its one-warp-CTA instantiation
+    (60,000), whose CTAs keep a batch in shared memory for all K turns.  Final state, outputs and statistics must be those
+    of step_agents called turn by turn, across in-place resets of both auto-reset modes and for rollouts of 1, 99 and 70
+    turns in a row."""
     A = evg._capi
-    cfg.auto_reset = 1
+    cfg.auto_reset = mode
     try:
         for a0, a1 in ((A.AGENT_RANDOM, A.AGENT_RANDOM), (A.AGENT_BASE_RUSH, A.AGENT_SWARM)):
-            g = evg.BatchedEvergladesEnv(n, seed=13, config=cfg, auto_reset=1, env_id_offset=2)
-            p = evg.BatchedEvergladesEnv(n, seed=13, config=cfg, auto_reset=1, env_id_offset=2)
+            g = evg.BatchedEvergladesEnv(n, seed=13, config=cfg, auto_reset=mode, env_id_offset=2)
+            p = evg.BatchedEvergladesEnv(n, seed=13, config=cfg, auto_reset=mode, env_id_offset=2)
             g.reset()
             p.reset()
-            g.rollout(170, a0, a1, graph_turns=50)   # 1 warm-up turn + 3 replays + 19 plain
+            launches = g.launch_count
+            for k in (1, 99, 70):
+                g.rollout(k, a0, a1)
+            assert g.launch_count - launches == 3   # one launch per rollout
             for _ in range(170):
                 p.step_agents(a0, a1)
             assert bool((g.obs == p.obs).all()) and bool((g.reward == p.reward).all()) and bool((g.done == p.done).all())
+            assert bool((g.status == p.status).all()) and bool((g.scores == p.scores).all())
             assert_states_equal(g.get_state(), p.get_state(), "after the rollout")
             sg, sp = g.episode_stats(), p.episode_stats()
-            sg.pop("env_turns"), sp.pop("env_turns")   # (the host-side turn counter does not see graph replays)
-            assert sg == sp and sg["episodes"] >= n
+            assert sg == sp and sg["episodes"] >= n and sg["env_turns"] == 170 * n
     finally:
         cfg.auto_reset = 0
 
