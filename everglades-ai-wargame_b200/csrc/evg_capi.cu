@@ -701,7 +701,7 @@ int evg_step_host_fmt(EvgSim* sim, int32_t format, const int8_t* h_actions, void
     // the D2H of one chunk (the PCIe-bound part) overlaps the H2D and the kernel of the next; everything is ordered
     // after what `stream` holds now, and `stream` waits for all of it — on the error paths too: whatever was
     // enqueued before a failure is joined into `stream` before the error is returned.
-    int chunks = 8;
+    int chunks = 16;  // (wire rows 2.66 -> 2.60 ms per 1 Mi matches against 8 chunks, int16 8.54 -> 8.25, float32 unchanged; tools/e2e_chunks.py)
     if (const char* c = getenv("EVG_HOST_CHUNKS")) chunks = atoi(c);
     if (chunks > 1 && sim->use_tpm && n >= 65536) {
         if (!sim->host_start) {

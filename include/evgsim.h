@@ -244,7 +244,7 @@ int evg_rollout(EvgSim* sim, int32_t agent_p0, int32_t agent_p1, int32_t n_turns
 /* Same turn through HOST buffers: H2D of the actions, the step, D2H of obs/reward/done, ordered after
  * what `stream` holds and complete when `stream` is (pinned host memory makes them truly asynchronous).
  * The device staging arrays are the caller's (same shapes as evg_step).  From 65,536 matches on, the
- * thread-per-match kernel runs the batch as EVG_HOST_CHUNKS (environment, default 8) sub-range launches on
+ * thread-per-match kernel runs the batch as EVG_HOST_CHUNKS (environment, default 16) sub-range launches on
  * two streams the library creates for this, so that the PCIe-bound D2H of one chunk hides the H2D and
  * the kernel of the next; results are those of evg_step. */
 int evg_step_host(EvgSim* sim, const int8_t* h_actions, float* h_obs, float* h_reward, uint8_t* h_done,
