@@ -823,12 +823,18 @@ __global__ void evg_agents_kernel(const __grid_constant__ Tables T, const uint32
 // q[i * row_stride + c * col_stride] is entry c of row i: row-major network output (row_stride = 12 * num_cols, col_stride = 1)
 // or the transposed layout evg_policy_mlp writes (row_stride = 1, col_stride = rows), which this thread-per-row scan reads
 // coalesced.  Every slot's best-Q only ever grows, so a candidate that does not beat the smallest of them is skipped at once.
-__global__ void evg_decode_dqn_kernel(const float* __restrict__ q, int num_cols, int player, int8_t* actions, int64_t n_envs, int64_t row_stride,
-                                      int64_t col_stride)
+// Lanes are different rows, so a branch taken by one lane is paid by all 32: per node the twelve candidates are first
+// tested against the smallest best-Q (uniform, cheap), then each lane walks only ITS OWN survivors in order (a slot's
+// best-Q only ever grows, so a candidate rejected by the first test stays rejected; survivors are re-tested) — the warp
+// runs max-over-lanes(survivors) insertions per node instead of one per candidate position that any lane accepts.
+constexpr int kDecodeThreads = 128;
+__global__ void __launch_bounds__(kDecodeThreads) evg_decode_dqn_kernel(const float* __restrict__ q, int num_cols, int player, int8_t* actions, int64_t n_envs,
+                                                                        int64_t row_stride, int64_t col_stride)
 {
+    __shared__ float vs[EVG_NUM_GROUPS][kDecodeThreads];  // this node's candidates, [group][thread]: a thread's own column, any index conflict-free
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int np_ = player < 0 ? 2 : 1;
-    if (i >= n_envs * np_) return;
+    if (i >= n_envs * np_) return;  // (no CTA barrier below: a thread only ever reads what it wrote itself)
     const int64_t env = i / np_;
     const int p = player < 0 ? (int)(i % np_) : player;
     const float* qi = q + i * row_stride;
@@ -841,21 +847,28 @@ __global__ void evg_decode_dqn_kernel(const float* __restrict__ q, int num_cols,
         float v[EVG_NUM_GROUPS];  // the twelve candidates of this node: independent loads in flight together
 #pragma unroll
         for (int g = 0; g < EVG_NUM_GROUPS; ++g) v[g] = __ldcs(qi + (int64_t)(g * num_cols + n) * col_stride);
+        uint32_t pm = 0;
 #pragma unroll
         for (int g = 0; g < EVG_NUM_GROUPS; ++g) {
-            if (!(v[g] > bmin)) continue;
+            pm |= (v[g] > bmin ? 1u : 0u) << g;
+            vs[g][threadIdx.x] = v[g];
+        }
+        for (; pm; pm &= pm - 1) {
+            const int g = __ffs(pm) - 1;
+            const float vg = vs[g][threadIdx.x];
+            if (!(vg > bmin)) continue;
             uint32_t eqm = 0, gtm = 0;  // slots that hold group g (`group_index in best_action_units`) / that v beats
 #pragma unroll
             for (int s = 0; s < EVG_MAX_ACTIONS; ++s) {
                 eqm |= (bu[s] == g ? 1u : 0u) << s;
-                gtm |= (v[g] > bq[s] ? 1u : 0u) << s;
+                gtm |= (vg > bq[s] ? 1u : 0u) << s;
             }
             const uint32_t ok = eqm ? (gtm & eqm) : gtm;  // a group already placed may only improve its own slot
             if (ok) {
                 const int s0 = __ffs(ok) - 1;  // the first slot in order that takes it
 #pragma unroll
                 for (int s = 0; s < EVG_MAX_ACTIONS; ++s)
-                    if (s == s0) { bq[s] = v[g]; bu[s] = g; bn[s] = n; }
+                    if (s == s0) { bq[s] = vg; bu[s] = g; bn[s] = n; }
                 bmin = bq[0];
 #pragma unroll
                 for (int s = 1; s < EVG_MAX_ACTIONS; ++s) bmin = fminf(bmin, bq[s]);
@@ -1003,7 +1016,7 @@ cudaError_t launch_decode_dqn(const float* q, int num_cols, int player, int8_t* 
 {
     const int64_t n = n_envs * (player < 0 ? 2 : 1);
     if (n <= 0) return cudaSuccess;
-    evg_decode_dqn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(q, num_cols, player, actions, n_envs,
+    evg_decode_dqn_kernel<<<(unsigned)((n + kDecodeThreads - 1) / kDecodeThreads), kDecodeThreads, 0, stream>>>(q, num_cols, player, actions, n_envs,
                                                                            transposed ? 1 : (int64_t)EVG_NUM_GROUPS * num_cols, transposed ? n : 1);
     return cudaGetLastError();
 }
