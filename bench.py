@@ -426,13 +426,26 @@ def main():
     probe_ms = d2h_probe(env.d2h_bytes_per_step(args.e2e_format))
     clocks.stop()
 
+    # ---- extra (not the metric): the same self-play as ONE launch per 150-turn rollout (evg_rollout: the batch stays in
+    # shared memory between turns, only the last turn's observations are written) — what a consumer that needs no
+    # per-turn observations gets (scripted evaluation matches, BASELINE.json configs[1] and [2])
+    KR = 150
+    env.rollout(10, evgsim._capi.AGENT_RANDOM, evgsim._capi.AGENT_RANDOM)
+    torch.cuda.synchronize(dev)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    env.rollout(KR, evgsim._capi.AGENT_RANDOM, evgsim._capi.AGENT_RANDOM)
+    r1.record(stream)
+    torch.cuda.synchronize(dev)
+    rollout_ms = r0.elapsed_time(r1)
+
     # ---- max over ranks
-    t = torch.tensor([total_ms, step_kernel_ms, e2e_ms, e2e_f32_ms, probe_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, step_kernel_ms, e2e_ms, e2e_f32_ms, probe_ms, rollout_ms], dtype=torch.float64, device=dev)
     f = torch.tensor([fought], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(f, op=dist.ReduceOp.SUM)
-    total_ms, step_kernel_ms, e2e_ms, e2e_f32_ms, probe_ms = (float(x) for x in t.tolist())
+    total_ms, step_kernel_ms, e2e_ms, e2e_f32_ms, probe_ms, rollout_ms = (float(x) for x in t.tolist())
     fought_all = int(f.item())
     stats = evd.gather_episode_stats(stats1, device=dev)  # the only collective; not timed
 
@@ -469,6 +482,9 @@ def main():
                          "bytes_formula": "1331 + 16 * fought unit slots per env-turn, slots counted on the device over the timed turns",
                          "kernel_ms": step_kernel_ms, "kernel_env_turns_per_s": E / (step_kernel_ms / 1e3)},
             "episode_stats": stats,
+            "scripted_rollout": {"value": total_envs * KR / (rollout_ms / 1e3), "unit": UNIT, "turns_per_launch": KR,
+                                 "note": "extra, not the metric: evg_rollout, one launch per 150 turns of the same self-play; "
+                                         "only the last turn's observations are written"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], line["cpu_baseline_port"] = cpu_baselines(args.cpu_seconds, args.seed)

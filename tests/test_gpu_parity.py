@@ -239,12 +239,14 @@ def test_masked_reset(evg, eo, cfg):
         assert np.array_equal(obs.cpu().numpy(), oobs.astype(np.float32)), t
 
 
-def test_random_agent_kernel_matches_oracle(evg, eo, cfg):
-    n = 300
+@pytest.mark.parametrize("n", [300, 301, 1027])  # (2n rows of 14 bytes leave the kernel in 16-byte pieces: with and without a tail)
+def test_random_agent_kernel_matches_oracle(evg, eo, cfg, n):
     env = evg.BatchedEvergladesEnv(n, seed=77, config=cfg, env_id_offset=5)
     env.reset()
     for turn in (1, 2):
         a = env.random_actions().cpu().numpy()
+        one = env.random_actions(player=1, out=env._actions.clone().zero_()).cpu().numpy()  # one player's rows only
+        assert np.array_equal(one[:, 1], a[:, 1]) and not one[:, 0].any()
         for i in range(n):
             for p in range(2):
                 want = eo.agent_random(cfg, 77, 5 + i, 0, turn, p)
