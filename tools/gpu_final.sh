@@ -9,7 +9,7 @@ python bench.py --phase staggered-match --no-cpu-baseline > $O/r2_bench_n1_stagg
 python bench.py --agents fused --no-cpu-baseline > $O/r2_bench_n1_agents_fused.json 2>/dev/null
 python bench.py --e2e-format i16 --no-cpu-baseline > $O/r2_bench_n1_e2e_i16.json 2>/dev/null
 python tools/per_turn_time.py > $O/r2_per_turn.json 2>/dev/null
-{ python tools/scripted_rollout.py 4096 900 random random; python tools/scripted_rollout.py 65536 450; python tools/scripted_rollout.py 1048576 300; } > $O/r2_scripted_rollout.jsonl 2>/dev/null
+{ python tools/scripted_rollout.py 4096 900 random random; python tools/scripted_rollout.py 65536 450; python tools/scripted_rollout.py 1048576 300; python tools/scripted_rollout.py 65536 450 random random; python tools/scripted_rollout.py 1048576 300 random random; } > $O/r2_scripted_rollout.jsonl 2>/dev/null
 { for a in "--policy dqn --dtype fp32 --graph" "--policy dqn --dtype bf16 --graph" "--policy dqn --fused --graph" "--policy dqn --fused" "--policy ppo --dtype bf16 --graph" "--policy rppo --dtype bf16 --graph"; do python tools/policy_rollout.py $a --turns 150; done; } > $O/r2_policy_rollout.jsonl 2>/dev/null
 python tools/mlp_time.py 32768 > $O/r2_mlp_time.jsonl 2>/dev/null
 # ncu: launch list of a short default-workload run, then one full capture of the step kernel at the bench's batch size
