@@ -190,6 +190,7 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
         }
     };
     int64_t step = 0;
+    bool l1_queued = false;  // the coming tile's first layer-1 MMAs were issued at the end of the previous tile
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kTileM;
         const int nrows = rows - row0 < kTileM ? (int)(rows - row0) : kTileM;
@@ -201,9 +202,10 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
         }
         for (int c = 0; c < n_chunks; ++c, ++step) {
             const int cn = c + 1 == n_chunks ? 0 : c + 1;  // the chunk of the next step
-            // ---- layer 1: D1 = A . W1c^T, as soon as W1c has landed
-            if (tid == 0) {
-                mbar_wait(&bar[2], ph_w1);
+            // ---- layer 1: D1 = A . W1c^T, as soon as W1c has landed.  Only a tile's first chunk is issued here: the later
+            // ones are queued right behind the previous chunk's layer 2 (below), so that their latency is not paid again
+            auto issue_layer1 = [&](uint32_t parity) {
+                mbar_wait(&bar[2], parity);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < kInPad / 16; ++k) {  // within a swizzle atom the start address advances by 32 bytes per K = 16
@@ -211,7 +213,9 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
                     umma(tmem + kTmemD1, make_desc(sA + offA), make_desc(sW1 + offB), idesc1, k > 0);
                 }
                 umma_commit(&bar[0]);
-            }
+            };
+            if (tid == 0 && c == 0 && !l1_queued) issue_layer1(ph_w1);
+            l1_queued = false;
             ph_w1 ^= 1;
             mbar_wait(&bar[0], ph_m1);  // D1 complete (and, the tensor pipe being in order, the previous step's layer 2: H is free)
             ph_m1 ^= 1;
@@ -252,11 +256,18 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
                     umma(tmem + kTmemD2, make_desc(sH + offA), make_desc(sW2 + offB), idesc2, (c > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&bar[1]);
+                // the next chunk's layer 1 behind it: every thread has finished reading D1 (barrier above), the tensor pipe
+                // runs in order, and W1's next chunk was requested when this chunk's layer 1 completed
+                if (c + 1 < n_chunks) issue_layer1(ph_w1);
             }
             ph_w2 ^= 1;
-            if (fetch_next_a) {  // the next tile's A, converted while layer 2 runs; made visible by the fence + barrier after the Q store
+            if (fetch_next_a) {  // the next tile's A, converted while layer 2 runs
                 store_a();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                // ... and its first layer-1 MMAs queued now: they only write D1, so they run under this tile's Q store
+                if (tid == 0) issue_layer1(ph_w1);
+                l1_queued = true;
             }
             mbar_wait(&bar[1], ph_m2);  // the W2 buffer is free again; after the last chunk D2 is complete
             ph_m2 ^= 1;
