@@ -228,18 +228,21 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
             }
             // ---- hidden activations of my row, my 48 of the chunk's 192 columns: TMEM -> registers -> ReLU, bf16 -> swizzled H
             {
+                constexpr int kLd = kChunk / 4 / 16;  // tensor-memory loads of 16 columns per thread: all issued, then one wait
+                uint32_t v[kLd][16];
+                const int jq1 = quarter * (kChunk / 4);
 #pragma unroll
-                for (int j0 = quarter * (kChunk / 4); j0 < (quarter + 1) * (kChunk / 4); j0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(lane_base + kTmemD1 + j0, v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int t = 0; t < kLd; ++t) tmem_ld16(lane_base + kTmemD1 + jq1 + 16 * t, v[t]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int t = 0; t < kLd; ++t) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {  // 8 hidden units = one 16-byte chunk of the swizzled row
                         uint32_t w[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            w[e] = pack_bf16(fmaxf(__uint_as_float(v[8 * g + 2 * e]), 0.f), fmaxf(__uint_as_float(v[8 * g + 2 * e + 1]), 0.f));
-                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, j0 + 8 * g)) = make_uint4(w[0], w[1], w[2], w[3]);
+                            w[e] = pack_bf16(fmaxf(__uint_as_float(v[t][8 * g + 2 * e]), 0.f), fmaxf(__uint_as_float(v[t][8 * g + 2 * e + 1]), 0.f));
+                        *reinterpret_cast<uint4*>(smem + kSmH + swz_offset(kTileM, r, jq1 + 16 * t + 8 * g)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -279,18 +282,17 @@ evg_policy_mlp_kernel(const float* __restrict__ obs, int64_t rows, int in_dim, c
             float* qp = q + (row0 + r) * q_row_stride + (int64_t)(quarter * (kOutPad / 4)) * q_col_stride;
             const int jq = quarter * (kOutPad / 4);
             const bool live = r < nrows;
-#pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(lane_base + kTmemD2 + jq + j0, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int e = 0; e < 16; ++e, qp += q_col_stride)
-                    if (live && jq + j0 + e < out_dim) *qp = __uint_as_float(v[e]);
-            }
-            uint32_t v4[4];
+            uint32_t v[2][16], v4[4];
+            tmem_ld16(lane_base + kTmemD2 + jq, v[0]);
+            tmem_ld16(lane_base + kTmemD2 + jq + 16, v[1]);
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v4[0]), "=r"(v4[1]), "=r"(v4[2]), "=r"(v4[3]) : "r"(lane_base + kTmemD2 + jq + 32));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 16) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e, qp += q_col_stride)
+                    if (live && jq + j0 + e < out_dim) *qp = __uint_as_float(v[j0 >> 4][e]);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e, qp += q_col_stride)
                 if (live && jq + 32 + e < out_dim) *qp = __uint_as_float(v4[e]);
