@@ -156,9 +156,11 @@ __device__ __noinline__ void load_rows_direct(const StepArgs& A, uint32_t* wrow,
 // leaves that code out, the kernel's instruction footprint being what its instruction cache misses are made of
 // THREADS: 128 (a CTA = 4 warps sharing tables, barrier and instruction stream), or 32 for small batches: one warp
 // per CTA spreads a few thousand matches over all SMs instead of a fifth of them.
+// ROLL (with AGENTS, both players scripted): the launch plays A.n_turns game turns per batch (evg_rollout); a separate
+// instantiation because the loop around the turn costs the single-turn kernel 4 % (0.544 vs 0.569 ms per 1 Mi matches)
 // WIRE: the observation output is the packed wire row of include/evgsim.h (EVG_OBS_WIRE: 128 bytes per match on DemoMap,
 // both players' observations + rewards + done in one cache line) instead of float32[2][obs_len] (840 bytes)
-template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS, int THREADS, bool WIRE = false>
+template <int NODES, int MAXSZ, typename HistT, int PITCH, bool AGENTS, int THREADS, bool WIRE = false, bool ROLL = false>
 __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_CTAS : EVG_TPM_LITE_MIN_CTAS) evg_step_tpm_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -291,11 +293,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     bool reset_now = false;
     // Fully scripted self-play (evg_rollout): the batch stays in its rows for A.n_turns game turns — only the last one
     // pays for the observations and the record write-back, none for a launch.  Every other call runs the body once.
-    const int n_turns = AGENTS ? A.n_turns : 1;
+    const int n_turns = ROLL ? A.n_turns : 1;
 #pragma unroll 1
     for (int tt = 0; tt < n_turns; ++tt) {
-    const bool last = !AGENTS || tt + 1 == n_turns;
-    if (AGENTS) { s0 = 0; s1 = 0; status = 0; }
+    const bool last = !ROLL || tt + 1 == n_turns;
+    if (ROLL) { s0 = 0; s1 = 0; status = 0; }
     if (valid) {
         turn = R[kRecTurn] + 1u;  // server.py:214
         episode = R[kRecEpisode];
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
         turn = 0;
         episode += 1;
     }
-    if (AGENTS && !last) {  // on to the next turn of the rollout (nobody sees this turn's terminal observation)
+    if (ROLL && !last) {  // on to the next turn of the rollout (nobody sees this turn's terminal observation)
         if (reset_now && S.auto_reset == EVG_AUTORESET_TERMINAL) {
             reset_row(S, R, n_nodes);
             turn = 0;
@@ -943,12 +945,16 @@ cudaError_t tpm_prepare(const Tables& t, int threads, size_t* smem_out, int* blo
         if (pick(t) != V_FAST) return cudaErrorInvalidValue;
         EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads)
         EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads)
+        EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads, false, true)
         EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads, true)
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, evg_step_tpm_kernel<11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads>,
                                                              threads, smem);
     }
     EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmThreads)
     EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, true, kTpmThreads)
+    EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, true, kTpmThreads, false, true)
+    EVG_TPM_ATTR(0, 16, uint8_t, 0, true, kTpmThreads, false, true)
+    EVG_TPM_ATTR(0, 16, uint16_t, 0, true, kTpmThreads, false, true)
     EVG_TPM_ATTR(11, 12, uint8_t, kFastPitch, false, kTpmThreads, true)
     EVG_TPM_ATTR(0, 16, uint8_t, 0, true, kTpmThreads)
     EVG_TPM_ATTR(0, 16, uint16_t, 0, true, kTpmThreads)
@@ -970,6 +976,8 @@ cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, siz
 {
     const bool agents = a.agent[0] != EVG_AGENT_EXTERNAL || a.agent[1] != EVG_AGENT_EXTERNAL;
     const bool wire = a.obs_fmt == EVG_OBS_WIRE;
+    const bool roll = a.n_turns > 1;  // (evg_rollout: both players scripted, float32 observations)
+    if (roll && (wire || a.agent[0] == EVG_AGENT_EXTERNAL || a.agent[1] == EVG_AGENT_EXTERNAL)) return cudaErrorInvalidValue;
     Variant v = pick(t);
     if (v == V_FAST && agents && wire) {
         v = V_GENERIC8;
@@ -981,17 +989,21 @@ cudaError_t launch_step_tpm(const Tables& t, const StepArgs& a, int threads, siz
 #define EVG_TPM_LAUNCH(...) evg_step_tpm_kernel<__VA_ARGS__><<<grid, threads, smem, stream>>>(t, a)
     if (v == V_FAST && threads == kTpmSmallThreads) {
         if (wire) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads, true);
+        else if (roll) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads, false, true);
         else if (agents) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, true, kTpmSmallThreads);
         else EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmSmallThreads);
     } else if (v == V_FAST) {
         if (wire) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmThreads, true);
+        else if (roll) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, true, kTpmThreads, false, true);
         else if (agents) EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, true, kTpmThreads);
         else EVG_TPM_LAUNCH(11, 12, uint8_t, kFastPitch, false, kTpmThreads);
     } else if (v == V_GENERIC8) {
         if (wire) EVG_TPM_LAUNCH(0, 16, uint8_t, 0, true, kTpmThreads, true);
+        else if (roll) EVG_TPM_LAUNCH(0, 16, uint8_t, 0, true, kTpmThreads, false, true);
         else EVG_TPM_LAUNCH(0, 16, uint8_t, 0, true, kTpmThreads);
     } else {
         if (wire) EVG_TPM_LAUNCH(0, 16, uint16_t, 0, true, kTpmThreads, true);
+        else if (roll) EVG_TPM_LAUNCH(0, 16, uint16_t, 0, true, kTpmThreads, false, true);
         else EVG_TPM_LAUNCH(0, 16, uint16_t, 0, true, kTpmThreads);
     }
 #undef EVG_TPM_LAUNCH
