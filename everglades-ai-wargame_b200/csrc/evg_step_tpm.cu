@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
     // SEG (compile-time map): combat applies damage in segments of 8 unit slots, a group of 9..MAXSZ slots on two lanes
     constexpr bool SEG = NODES != 0 && EVG_TPM_SEG != 0 && MAXSZ > 8;
     constexpr int HVN = SEG ? 8 : MAXSZ;
-    constexpr bool PIPE = NODES != 0 && EVG_TPM_PIPE != 0 && !LITE;
+    constexpr bool PIPE = NODES != 0 && EVG_TPM_PIPE != 0 && !LITE && !ROLL;  // (a rollout loads records once per K turns: the pipeline's 71 registers are worth more to its turns)
     uint4 nxt[16];
     uint32_t nxa[7];
     bool have = false;

@@ -189,3 +189,30 @@ def test_demomap_loadouts_with_groups_split_over_two_lanes(sizes, lite, monkeypa
     assert deaths > 0
     st = env.episode_stats()
     assert st["episodes"] >= 2 * n and st["fought_unit_slots"] == eo.fought_slots()
+
+
+@pytest.mark.parametrize("budget", [100, 192])
+def test_multi_turn_rollout_on_another_map(tmp_path, budget, monkeypatch):
+    """evg_rollout's K-turns-per-launch path in the run-time-sized instantiations (7-node map, byte and 16-bit damage
+    histograms): same state, outputs and statistics as evg_step_agents turn by turn, with in-place resets (turn limit 60)."""
+    monkeypatch.setenv("EVG_STEP_KERNEL", "tpm")
+    import __graft_entry__ as g
+    g.build()
+    import evgsim
+
+    A = evgsim._capi
+    d = write_configs(tmp_path, budget)
+    cfg = evgsim.load_config(d, "Map7.json", "Units4.json", "Setup.json", auto_reset=1)
+    n = 1500
+    for a0, a1 in ((A.AGENT_RANDOM, A.AGENT_SWARM), (A.AGENT_BASE_RUSH, A.AGENT_RANDOM)):
+        r = evgsim.BatchedEvergladesEnv(n, seed=budget, config=cfg, auto_reset=1, env_id_offset=4)
+        p = evgsim.BatchedEvergladesEnv(n, seed=budget, config=cfg, auto_reset=1, env_id_offset=4)
+        r.reset()
+        p.reset()
+        r.rollout(47, a0, a1)
+        r.rollout(90, a0, a1)
+        for _ in range(137):
+            p.step_agents(a0, a1)
+        assert bool((r.obs == p.obs).all()) and bool((r.reward == p.reward).all()) and bool((r.done == p.done).all())
+        assert_states_equal(r.get_state(), p.get_state(), "after the rollout")
+        assert r.episode_stats() == p.episode_stats() and r.episode_stats()["episodes"] >= 2 * n
