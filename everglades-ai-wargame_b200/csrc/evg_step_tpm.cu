@@ -40,7 +40,13 @@
 #include "evg_step_common.cuh"
 
 #ifndef EVG_TPM_MOVE_UNROLL
-#define EVG_TPM_MOVE_UNROLL 2
+#define EVG_TPM_MOVE_UNROLL 1  // (1: 0.4965 ms, 2: 0.4983, 3: 0.5016, 4: 0.5078 per 1 Mi match-turns; footprint beats overlap)
+#endif
+#ifndef EVG_TPM_STORE_UNROLL
+#define EVG_TPM_STORE_UNROLL 8  // record store, 16 chunks per lane (8: 0.4882 ms, 4: 0.4904, 2: 0.4922, 16: 0.4924)
+#endif
+#ifndef EVG_TPM_STREAM_UNROLL
+#define EVG_TPM_STREAM_UNROLL 4  // streaming loop of an observation window, 16 iterations (4: 0.4924 ms, 8: 0.4942, 16: 0.4965, 2: 0.4971)
 #endif
 #ifndef EVG_TPM_CAPTURE_UNROLL
 #define EVG_TPM_CAPTURE_UNROLL 1
@@ -69,7 +75,7 @@ namespace evg {
 
 namespace {
 
-constexpr int kMoveUnroll = EVG_TPM_MOVE_UNROLL, kCaptureUnroll = EVG_TPM_CAPTURE_UNROLL;
+constexpr int kMoveUnroll = EVG_TPM_MOVE_UNROLL, kCaptureUnroll = EVG_TPM_CAPTURE_UNROLL, kStreamUnroll = EVG_TPM_STREAM_UNROLL, kStoreUnroll = EVG_TPM_STORE_UNROLL;
 
 // game_init state (server.py:133-209) for one match: its record row in shared memory (the health refill is the warp's
 // job: refill_health below)
@@ -833,7 +839,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
                 const uint32_t* srow = wrow + stage_off + 2 * cp;
                 uint32_t* orow = obs_base + 2 * pr;
                 if (nvalid == 32) {  // whole warp: no per-match predicates
-#pragma unroll
+#pragma unroll kStreamUnroll
                     for (int it = 0; it < 32 / MPI; ++it) {
                         const int m = MPI * it + sub;
                         const uint2 v = *reinterpret_cast<const uint2*>(srow + (size_t)m * P);
@@ -880,7 +886,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kTpmThreads ? EVG_TPM_MIN_
             g4[f] = make_uint4(a.x, a.y, b.x, b.y);
         };
         if (NODES && nvalid == 32) {
-#pragma unroll
+#pragma unroll kStoreUnroll
             for (int i = 0; i < (NODES ? 16 : 1); ++i) put(pl + 32 * i);
         } else {
 #pragma unroll 1
