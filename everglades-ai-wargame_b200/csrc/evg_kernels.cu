@@ -965,8 +965,8 @@ cudaError_t launch_reset(const Tables& t, uint32_t* records, double* health, con
 }
 
 // EVG_OBS_I16: the float32 observation vector narrowed to int16 (every entry is an integer that fits), 8 values per thread
-__global__ void evg_obs_to_i16_kernel(const float4* __restrict__ obs, uint4* __restrict__ out, const float* __restrict__ obs1,
-                                      int16_t* __restrict__ out1, int64_t n8, int64_t n)
+// (obs1 / out1 are the same arrays as obs / out, typed for the scalar tail: no __restrict__ on pointers that alias)
+__global__ void evg_obs_to_i16_kernel(const float4* obs, uint4* out, const float* obs1, int16_t* out1, int64_t n8, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n8) {
